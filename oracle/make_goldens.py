@@ -1,0 +1,199 @@
+"""TEST INFRASTRUCTURE ONLY.  Regenerates tests/golden/*.npz by running the UNMODIFIED reference
+modules (imported from the read-only checkout through oracle/ref_stubs.py) on seeded synthetic
+inputs.  The reference ships no tests or golden vectors of its own, so
+these fixtures are what pins the oracle (oracle/restate.py) and, through it, the CUDA path.
+
+    python -m oracle.make_goldens            # needs /root/reference; not runnable on the GPU box
+
+Inputs are never stored: they are re-derived from the seeds with codlad_b200.synthetic /
+codlad_b200.weights, which is also what the tests do.  Only reference OUTPUTS are stored.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_stubs  # noqa: E402
+
+ref_stubs.install()
+
+from codlad_b200 import synthetic, weights  # noqa: E402
+from diffusion_and_flow import create_diffusion  # noqa: E402
+import diffusion_and_flow.gaussian_diffusion as gd  # noqa: E402
+from models.latent_model import MPNN_models  # noqa: E402
+from models.vae_model import VAE, IC_Decoder, IC_Decoder_angle  # noqa: E402
+from utils.utils_ic import ic_to_xyz  # noqa: E402
+from utils.vq_module import VectorQuantizerEMA, build_quantize  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+C2_CKPT = os.path.join(ref_stubs.REFERENCE_ROOT, "results", "Vae_m1_12-23-23_12345", "model.pt")
+
+
+def ref_denoiser(k_neighbors=64, seed=0):
+    sd = weights.init_denoiser_state(seed)
+    m = MPNN_models["mpnn_diffusion"](input_size=3, unconditional=True, diffusion="diffusion", k_neighbors=k_neighbors).eval()
+    m.load_state_dict(sd, strict=True)        # also proves the key/shape inventory in weights.py
+    return m, sd
+
+
+def golden_denoiser(name, L, frames, k_neighbors, prot_seed, x_seed, t_list, lengths=None):
+    """One denoiser forward.  `lengths` (ragged case) builds a batch of proteins of different
+    length, padded by the reference's own reshape_and_create_mask."""
+    m, _ = ref_denoiser(k_neighbors)
+    if lengths is None:
+        prot = synthetic.make_protein(L, frames, seed=prot_seed)
+        batch = synthetic.collate(prot)
+        B, Lmax = frames, L
+        mask = torch.ones(B, Lmax, dtype=torch.bool)
+    else:
+        parts = [synthetic.collate(synthetic.make_protein(n, 1, seed=prot_seed + i)) for i, n in enumerate(lengths)]
+        batch = {"CG_nxyz": torch.cat([p["CG_nxyz"] for p in parts]), "num_CGs": torch.tensor(lengths),
+                 "CG_nbr_list": parts[0]["CG_nbr_list"]}
+        B, Lmax = len(lengths), max(lengths)
+        mask = torch.arange(Lmax)[None, :] < torch.tensor(lengths)[:, None]
+    x = synthetic.latent_noise((B, Lmax, 3), x_seed)
+    batch["randn"] = torch.zeros(B, Lmax)
+    t = torch.tensor(t_list, dtype=torch.int64)
+    with torch.no_grad():
+        X = torch.zeros(B, Lmax, 3)
+        off = 0
+        for b in range(B):
+            n = int(batch["num_CGs"][b])
+            X[b, :n] = batch["CG_nxyz"][off:off + n, 1:]
+            off += n
+        E, E_idx = m.features(X, mask.int(), torch.arange(Lmax)[None].expand(B, -1), torch.ones(B, Lmax))
+        D_nb, _, _ = m.features._dist(X, mask.int())
+        out = m(x, t, None, mask=mask, batch=batch)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), E_idx=E_idx.numpy().astype(np.int16), D_nb=D_nb.numpy(),
+                        E_sample=E[:, ::7, ::5].numpy(), out=out.numpy(),
+                        meta=np.array([L, frames, k_neighbors, prot_seed, x_seed] + list(t_list)))
+    print(name, "out", tuple(out.shape), float(out.abs().max()))
+
+
+def golden_sampler(name, L, prot_seed, z_seed, noise_seed, steps=100):
+    """Full p_sample_loop through SpacedDiffusion with the per-step noise injected."""
+    m, _ = ref_denoiser()
+    prot = synthetic.make_protein(L, 1, seed=prot_seed)
+    batch = synthetic.collate(prot)
+    batch["randn"] = torch.zeros(1, L)
+    mask = torch.ones(1, L, dtype=torch.bool)
+    z = synthetic.latent_noise((1, L, 3), z_seed)
+    noises = synthetic.latent_noise((steps, 1, L, 3), noise_seed)
+    diffusion = create_diffusion(str(steps))
+    order = list(range(steps))[::-1]
+    it = iter(order)
+    real = gd.th.randn_like
+    gd.th.randn_like = lambda x: noises[next(it)].to(x)      # reference draws at gaussian_diffusion.py:440
+    keep = {}
+    try:
+        with torch.no_grad():
+            for s, out in zip(order, diffusion.p_sample_loop_progressive(
+                    m.forward, z.shape, z, clip_denoised=False,
+                    model_kwargs=dict(y=None, mask=mask, batch=batch), device="cpu")):
+                if s in (steps - 1, steps // 2, 1, 0):
+                    keep[f"sample_{s}"] = out["sample"].numpy()
+    finally:
+        gd.th.randn_like = real
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), timestep_map=np.array(diffusion.timestep_map),
+                        meta=np.array([L, prot_seed, z_seed, noise_seed, steps]), **keep)
+    print(name, {k: float(np.abs(v).max()) for k, v in keep.items()})
+
+
+def export_c2_decoder():
+    ck = torch.load(C2_CKPT, map_location="cpu")
+    want = weights.ic_decoder_shapes(False)
+    out = {}
+    for k, shape in want.items():
+        assert tuple(ck[k].shape) == tuple(shape), k
+        out[k] = ck[k].float().numpy()
+    np.savez_compressed(os.path.join(OUT, "ic_decoder_c2.npz"), **out)
+    print("ic_decoder_c2", len(out), sum(v.size for v in out.values()))
+
+
+def decode_state(angle_variant, use_c2=False):
+    """Random-init (gain 0.5, angles O(1): coordinates are well conditioned) or, with use_c2, the
+    shipped C2 checkpoint's `equivaraintconv.*` tensors loaded into IC_Decoder (real weight
+    magnitudes; they drive angles to O(1e6) rad on synthetic inputs, so only ic_recon is compared,
+    with a relative tolerance)."""
+    sd = weights.init_vae_decode_state(0, angle_variant=angle_variant)
+    if use_c2:
+        c2 = np.load(os.path.join(OUT, "ic_decoder_c2.npz"))
+        for k in c2.files:
+            sd[k] = torch.from_numpy(c2[k])
+    return sd
+
+
+def golden_decode(name, L, frames, prot_seed, lat_seed, angle_variant, use_c2=False):
+    sd = decode_state(angle_variant, use_c2)
+    dec = (IC_Decoder_angle if angle_variant else IC_Decoder)(n_atom_basis=36, n_rbf=15, cutoff=21.0, num_conv=4, activation="swish")
+    vae = VAE(5, 36, encoder=None, quantize=build_quantize("vqvae", 4096, 3, 0.25, 0.99), equivaraintconv=dec, vqdim=3).eval()
+    res = vae.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and set(res.missing_keys) <= {"map_in.weight", "map_in.bias"}, res
+    prot = synthetic.make_protein(L, frames, seed=prot_seed)
+    batch = synthetic.collate(prot)
+    mean, std = (torch.tensor(v) for v in weights.LATENT_STATS[("N6", "PED")])
+    latent = mean + std * synthetic.latent_noise((frames, L, 3), lat_seed)
+    mask = torch.ones(frames, L, dtype=torch.bool)
+    with torch.no_grad():
+        _, ic_recon = vae.latent_decode(latent, mask, batch)
+        xyz = ic_to_xyz(batch["OG_CG_nxyz"].reshape(-1, L + 2, 4), ic_recon.reshape(-1, L, 13, 3), prot.info)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ic_recon=ic_recon.numpy(), xyz=xyz.numpy(),
+                        meta=np.array([L, frames, prot_seed, lat_seed, int(angle_variant)]))
+    print(name, "ic", tuple(ic_recon.shape), "xyz", tuple(xyz.shape), float(ic_recon[..., 1:].abs().max()))
+
+
+def golden_vq(name, n, seed):
+    """Index parity of the restated third-party VQ against the in-repo VectorQuantizerEMA
+    (utils/vq_module.py:56-71), the only reference-side implementation that exists offline."""
+    sd = weights.init_vae_decode_state(0)
+    cb = sd["quantize._codebook.embed"][0]
+    vq = VectorQuantizerEMA(4096, 3, 0.25, 0.99).eval()
+    vq.embeddings.copy_(cb)
+    mean, std = (torch.tensor(v) for v in weights.LATENT_STATS[("N6", "PED")])
+    x = mean + std * synthetic.latent_noise((n, 3), seed)
+    with torch.no_grad():
+        _, idx, _ = vq(x[None])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), idx=idx.numpy().astype(np.int16), meta=np.array([n, seed]))
+    print(name, idx.shape)
+
+
+def golden_ic_large_angle(name, L, seed):
+    """ic_to_xyz alone with angles of magnitude up to 1e5 rad (random-init decoders produce such
+    values, SURVEY 'hard parts'): full-range sin/cos reduction must agree."""
+    prot = synthetic.make_protein(L, 2, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    ic = torch.randn(2, L, 13, 3, generator=g)
+    ic[..., 0] = 1.0 + 0.5 * torch.rand(2, L, 13, generator=g)
+    ic[..., 1:] *= torch.tensor([1.0, 1e2, 1e5])[torch.randint(0, 3, (2, L, 13, 1), generator=g)].expand(-1, -1, -1, 2)
+    batch = synthetic.collate(prot)
+    with torch.no_grad():
+        xyz = ic_to_xyz(batch["OG_CG_nxyz"].reshape(-1, L + 2, 4), ic, prot.info)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ic=ic.numpy(), xyz=xyz.numpy(), meta=np.array([L, seed]))
+    print(name, tuple(xyz.shape))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    export_c2_decoder()
+    golden_denoiser("denoiser_L64_B1", 64, 1, 64, 1001, 2001, [717])
+    golden_denoiser("denoiser_L70_B2", 70, 2, 64, 1002, 2002, [999, 10])
+    golden_denoiser("denoiser_L100_K48", 100, 1, 48, 1004, 2004, [505])
+    golden_denoiser("denoiser_L40_short", 40, 2, 64, 1006, 2006, [0, 303])           # K = L < 64
+    golden_denoiser("denoiser_ragged", 80, 0, 64, 1005, 2005, [61, 989], lengths=[80, 70])
+    golden_sampler("sampler_L64_100", 64, 1001, 2001, 3001, 100)
+    golden_decode("decode_L64_N6", 64, 2, 1001, 4001, False)
+    golden_decode("decode_L64_K4", 64, 1, 1001, 4002, True)
+    golden_decode("decode_L64_N6_c2", 64, 1, 1001, 4003, False, use_c2=True)
+    golden_vq("vq_20000", 20000, 5001)
+    golden_ic_large_angle("ic_large_angle_L48", 48, 6001)
+
+
+if __name__ == "__main__":
+    main()
