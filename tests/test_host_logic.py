@@ -1,0 +1,81 @@
+"""CPU: host-side logic of the product package (schedule tables, topology tables, batch -> FrameSet
+conversion, weight inventories) against the oracle / the committed goldens."""
+import numpy as np
+import torch
+
+from codlad_b200 import diffusion, sampler, synthetic, topology, weights
+from oracle import restate as R
+from tests import parity_utils as P
+
+
+def test_schedule_tables_match_oracle_and_reference_golden():
+    d = diffusion.create_diffusion("100")
+    s = R.respaced_schedule(100)
+    assert np.array_equal(np.array(d.timestep_map), s["timestep_map"])
+    assert np.array_equal(np.array(d.timestep_map), P.golden("sampler_L64_100")["timestep_map"])
+    c = d.coef_table()
+    for col, key in enumerate(["post_logvar_clipped", "log_betas", "sqrt_recip_ac", "sqrt_recipm1_ac", "post_coef1", "post_coef2"]):
+        assert np.array_equal(c[:, col], s[key].astype(np.float32)), key
+    assert c[0, 6] == 0 and (c[1:, 6] == 1).all()
+    for n in ("1", "10", "250", "ddim50", "10,20"):
+        dd = diffusion.create_diffusion(n)
+        assert dd.num_timesteps == len(dd.timestep_map)
+    assert sorted(diffusion.space_timesteps(1000, "100")) == R.kept_timesteps(100)
+
+
+def test_weight_inventories():
+    d = weights.denoiser_shapes()
+    assert len(d) == 108 and sum(int(np.prod(s)) for s in d.values()) == 2449974
+    assert sum(int(np.prod(s)) for s in weights.ic_decoder_shapes(False).values()) == 43394
+    assert sum(int(np.prod(s)) for s in weights.ic_decoder_shapes(True).values()) == 51044
+    c2 = P.golden("ic_decoder_c2")
+    assert sorted(c2.files) == sorted(weights.ic_decoder_shapes(False))
+
+
+def test_topology_tables():
+    assert topology.NUM_RESTYPES == 22 and int(topology.ATOM_COUNT.max()) == 14
+    for rid in range(22):
+        n_side = int(topology.ATOM_COUNT[rid]) - 4
+        for s in range(10):
+            tri = topology.ORDERS[rid, s]
+            if s < n_side:
+                assert int(tri.max()) < 4 + s, "an atom may only be built from atoms placed before it"
+            else:
+                assert tri.tolist() == [0, 1, 2]
+    rt = torch.tensor([3, 13, 2, 16])
+    permute, atom_idx, orders = topology.build_info(rt)
+    assert permute.numel() == 4 + 14 + 5 + 7 and orders.shape == (10, 4, 3)
+    inv = topology.slot_to_atom_map((permute, atom_idx, orders), 4)
+    assert (inv >= 0).sum() == permute.numel() and inv[4] == -1 and inv[14] == 4
+
+
+def test_frames_from_batch_matches_oracle_graph():
+    prot = synthetic.make_protein(50, 3, seed=9)
+    batch = synthetic.collate(prot)
+    fs = sampler.frames_from_batch(batch, prot.info, num_ensemble=2)
+    assert fs.F == 3 and fs.NB == 6 and fs.L == 50 and fs.total_atoms == 6 * prot.num_atoms
+    assert torch.equal(fs.X, prot.ca_full[:, 1:-1]) and torch.equal(fs.ca_full, prot.ca_full)
+    assert fs.frame_of.tolist() == [0, 1, 2, 0, 1, 2]
+    nbr = R.directed_edges(batch["CG_nbr_list"])
+    want = set(map(tuple, nbr.tolist()))
+    got = set()
+    for r in range(fs.F * fs.L):
+        f = r // fs.L
+        for e in range(int(fs.csr_row[r]), int(fs.csr_row[r + 1])):
+            got.add((r, f * fs.L + int(fs.csr_col[e])))
+    assert got == want
+    for r in range(fs.F * fs.L):
+        seg = fs.csr_col[int(fs.csr_row[r]):int(fs.csr_row[r + 1])]
+        assert bool((seg[1:] > seg[:-1]).all())
+
+
+def test_frames_from_batch_ragged():
+    prots = [synthetic.make_protein(n, 1, seed=30 + i) for i, n in enumerate((40, 25))]
+    parts = [synthetic.collate(p) for p in prots]
+    batch = {k: torch.cat([p[k] for p in parts]) for k in ("CG_nxyz", "OG_CG_nxyz", "num_CGs")}
+    batch["CG_nbr_list"] = torch.cat([parts[0]["CG_nbr_list"], parts[1]["CG_nbr_list"] + 40])
+    fs = sampler.frames_from_batch(batch, [p.info for p in prots], 1)
+    assert fs.L == 40 and fs.lengths.tolist() == [40, 25]
+    assert torch.equal(fs.X[1, :25], prots[1].ca_full[0, 1:-1]) and float(fs.X[1, 25:].abs().sum()) == 0
+    assert int(fs.csr_row[40 + 25]) == int(fs.csr_row[-1])          # padded rows have no edges
+    assert fs.out_off.tolist() == [0, prots[0].num_atoms]
