@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcodlad_b200.so")
 ABI_VERSION = 1
 
-PRECISION = {"fp32": 0, "f32": 0, "bf16": 1}
+PRECISION = {"fp32": 0, "f32": 0, "f16": 1, "fp16": 1}
 
 
 class cb2_tensor(C.Structure):

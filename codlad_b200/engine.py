@@ -96,10 +96,10 @@ class Plan:
 
     # -- geometry ------------------------------------------------------------------------------
     def set_frames(self, X, lengths, cg_z, frame_of):
-        X = X.to(self.device, torch.float32).contiguous()
-        lengths = lengths.to(self.device, torch.int32).contiguous()
-        cg_z = cg_z.to(self.device, torch.int32).contiguous()
-        frame_of = frame_of.to(self.device, torch.int32).contiguous()
+        X = X.to(self.device, torch.float32, non_blocking=True).contiguous()
+        lengths = lengths.to(self.device, torch.int32, non_blocking=True).contiguous()
+        cg_z = cg_z.to(self.device, torch.int32, non_blocking=True).contiguous()
+        frame_of = frame_of.to(self.device, torch.int32, non_blocking=True).contiguous()
         assert X.shape == (self.F, self.L, 3) and cg_z.shape == (self.F, self.L)
         assert lengths.shape == (self.F,) and frame_of.shape == (self.NB,)
         N.check(N.lib().cb2_plan_set_frames(self.handle, N.dptr(X), N.dptr(lengths), N.dptr(cg_z), N.dptr(frame_of), N.stream_ptr()),
@@ -108,7 +108,7 @@ class Plan:
         self._frame_of = frame_of
 
     def set_topology(self, vae: VaeEngine, ca_full, csr_row, csr_col, orders, slot_atom, out_off):
-        ca_full = ca_full.to(self.device, torch.float32).contiguous()
+        ca_full = ca_full.to(self.device, torch.float32, non_blocking=True).contiguous()
         assert ca_full.shape == (self.F, self.L + 2, 3)
         csr_row = csr_row.to(torch.int32).cpu().contiguous()
         csr_col = csr_col.to(torch.int32).cpu().contiguous()
@@ -163,7 +163,7 @@ class Plan:
     # -- debug -------------------------------------------------------------------------------------
     def buffer(self, name: str) -> torch.Tensor:
         """Copy of a plan-owned buffer (parity tests)."""
-        edge_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        edge_dtype = torch.float16 if N.PRECISION[self.precision] == 1 else torch.float32
         spec = {
             "nbr_idx": (torch.int32, (self.F, self.L, self.K)), "nbr_dist": (torch.float32, (self.F, self.L, self.K)),
             "E": (torch.float32, (self.F, self.L, self.K, 128)), "hE0": (edge_dtype, (self.F, self.L, self.K, 128)),

@@ -44,6 +44,19 @@ class FrameSet:
         self.out_off = torch.cumsum(na, 0) - na
         self.total_atoms = int(na.sum())
 
+    _HOST_FIELDS = ("X", "ca_full", "cg_z", "lengths", "csr_row", "csr_col", "orders", "slot_atom", "frame_of", "out_off")
+
+    def pin(self):
+        """Page-lock the host tensors so uploads are true async DMA (what bench.py's e2e leg times)."""
+        for name in self._HOST_FIELDS:
+            t = getattr(self, name).contiguous()
+            setattr(self, name, t.pin_memory() if torch.cuda.is_available() and not t.is_pinned() else t)
+        return self
+
+    def host_bytes(self) -> int:
+        """Bytes copied host -> device by Backmapper.upload()."""
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self._HOST_FIELDS)
+
     @property
     def F(self): return self.X.shape[0]
     @property
@@ -107,7 +120,8 @@ def frames_from_batch(batch: dict, infos, num_ensemble: int = 1) -> FrameSet:
         cols.append(col)
         e_base += int(col.numel())
     frame_of = torch.arange(F, dtype=torch.int32).repeat(num_ensemble)
-    return FrameSet(X, ca_full, cg_z, num.to(torch.int32), torch.cat(rows), torch.cat(cols) if cols else torch.zeros(0, dtype=torch.int32),
+    return FrameSet(X, ca_full, cg_z, num.to(torch.int32), torch.cat(rows).to(torch.int32),
+                    torch.cat(cols).to(torch.int32) if cols else torch.zeros(0, dtype=torch.int32),
                     orders, slot_atom, num_atoms, frame_of)
 
 
@@ -115,7 +129,7 @@ class Backmapper:
     """CG trace -> all-atom ensemble: 100-step latent diffusion + VQ-VAE decode + IC reconstruction."""
 
     def __init__(self, denoiser_state: dict, vae_state: dict, vae_type: str = "N6", k_neighbors: int = 64,
-                 num_sampling_steps: int = 100, precision: str = "bf16", latent_stats=None):
+                 num_sampling_steps: int = 100, precision: str = "f16", latent_stats=None):
         self.precision = precision
         self.denoiser = DenoiserEngine(denoiser_state, k_neighbors)
         stats = latent_stats or weights.LATENT_STATS[(vae_type, VAE_DATA[vae_type])]
@@ -124,6 +138,7 @@ class Backmapper:
         self.T = self.diffusion.num_timesteps
         self._plans = {}
         self._bufs = {}
+        self._host_xyz = {}
 
     def plan_for(self, fs: FrameSet, keep_debug: bool = False) -> Plan:
         key = (fs.F, fs.NB, fs.L, keep_debug)
@@ -164,8 +179,14 @@ class Backmapper:
         idx, zq, ic, xyz = plan.decode(self.vae, x, denorm=True, num_atoms_total=fs.total_atoms)
         return {"latent": x, "idx": idx, "zq": zq, "ic_recon": ic, "xyz": xyz}
 
-    def backmap_host(self, fs: FrameSet, z=None, step_noise=None):
-        """End-to-end call with HOST inputs and HOST coordinates out (what bench.py's e2e times)."""
+    def backmap_host(self, fs: FrameSet, z=None, step_noise=None, generator: torch.Generator = None):
+        """End-to-end call with HOST inputs and HOST coordinates out (what bench.py's e2e times):
+        H2D of the frame set, per-frame precompute, T-step sampling, decode, D2H of [sum Na, 3]."""
         plan = self.upload(fs)
-        out = self.sample(plan, fs, z, step_noise)
-        return out["xyz"].cpu()
+        out = self.sample(plan, fs, z, step_noise, generator=generator)
+        host = self._host_xyz.get(fs.total_atoms)
+        if host is None:
+            host = self._host_xyz[fs.total_atoms] = torch.empty(fs.total_atoms, 3, dtype=torch.float32).pin_memory()
+        host.copy_(out["xyz"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host

@@ -31,6 +31,15 @@ import torch.nn.functional as F
 H = 128  # hidden width of the denoiser (models/latent_model.py:80-84)
 
 
+def sqrt_rn(t: torch.Tensor) -> torch.Tensor:
+    """IEEE correctly-rounded fp32 square root (numpy -> hardware sqrtps).  torch.sqrt on the
+    AVX512 CPU build of torch 2.11 is NOT correctly rounded (1 ulp low on ~0.6 % of inputs,
+    measured against float64 and against torch.sqrt on CUDA, which is correctly rounded), so the
+    places where this oracle promises bit-exact results (k-NN distances, VQ distances) use this
+    helper: it is what the reference computes on its own target (a CUDA device)."""
+    return torch.from_numpy(np.sqrt(t.detach().contiguous().numpy()))
+
+
 # --------------------------------------------------------------------------------------
 # Diffusion schedule (float64 numpy, like the reference)
 # --------------------------------------------------------------------------------------
@@ -121,7 +130,7 @@ def knn_graph(X, mask, k_neighbors):
     sq = d * d
     s = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
     m2 = m[:, None, :] * m[:, :, None]
-    D = m2 * torch.sqrt(s + 1e-6)
+    D = m2 * sqrt_rn(s + 1e-6)
     Dmax = D.max(-1, keepdim=True).values
     Dadj = D + (1.0 - m2) * Dmax
     vals, idx = torch.sort(Dadj, dim=-1, stable=True)
@@ -335,7 +344,7 @@ def vq_nearest(x, codebook):
     for s in range(0, x.shape[0], 8192):
         xc = x[s:s + 8192]
         xy = ((xc[:, None, 0] * e[None, :, 0] + xc[:, None, 1] * e[None, :, 1]) + xc[:, None, 2] * e[None, :, 2]) * -2.0
-        d = torch.sqrt(((x2[s:s + 8192, None] + e2[None, :]) + xy).clamp(min=0))
+        d = sqrt_rn(((x2[s:s + 8192, None] + e2[None, :]) + xy).clamp(min=0))
         out[s:s + 8192] = torch.argmax(-d, dim=-1)
     return out
 
