@@ -36,6 +36,7 @@ SIGNATURES = {
     "cb2_plan_launches": (_LL, [_P]),
     "cb2_plan_set_frames": (_I, [_P, _P, _P, _P, _P, _P]),
     "cb2_plan_forward": (_I, [_P, _P, _P, _P, _P]),
+    "cb2_plan_forward_partial": (_I, [_P, _P, _P, _I, _P]),
     "cb2_plan_set_schedule": (_I, [_P, _P, _P, _I, _P]),
     "cb2_plan_sample": (_I, [_P, _P, _P, _I, _P]),
     "cb2_plan_set_topology": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P]),

@@ -63,14 +63,14 @@ struct Packer {
     }
 };
 
-struct BfPacker {
-    std::vector<__nv_bfloat16> buf;
-    // dst[o][k] = bf16(scale * W[o][col0 + k]), 128 x 128
+struct HalfPacker {
+    std::vector<__half> buf;
+    // dst[o][k] = fp16(scale * W[o][col0 + k]), one 128 x 128 block (consecutive blocks are 128 rows apart)
     size_t block(const float* W, int in_total, int col0, float scale = 1.0f) {
-        size_t off = (buf.size() + 511) & ~(size_t)511;   // 1 KiB alignment
+        size_t off = buf.size();
         buf.resize(off + 128 * 128);
         for (int o = 0; o < 128; ++o)
-            for (int k = 0; k < 128; ++k) buf[off + (size_t)o * 128 + k] = __float2bfloat16(scale * W[(size_t)o * in_total + col0 + k]);
+            for (int k = 0; k < 128; ++k) buf[off + (size_t)o * 128 + k] = __float2half_rn(scale * W[(size_t)o * in_total + col0 + k]);
         return off;
     }
 };
@@ -121,7 +121,7 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
     if (!tensors || !freqs128 || !out) { set_error("denoiser_create: null argument"); return 1; }
     TensorTable tt(tensors, n_tensors);
     Packer pk;
-    BfPacker bp;
+    HalfPacker bp;
     const int H = CB2_H;
     std::map<std::string, size_t> off;
     std::map<std::string, size_t> boff;
@@ -231,10 +231,11 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
     m.k_neighbors = k_neighbors;
     CB2_CUDA(cudaMalloc(&m.dev_f32, pk.buf.size() * sizeof(float)));
     CB2_CUDA(cudaMemcpy(m.dev_f32, pk.buf.data(), pk.buf.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CB2_CUDA(cudaMalloc(&m.dev_bf16, bp.buf.size() * sizeof(__nv_bfloat16)));
-    CB2_CUDA(cudaMemcpy(m.dev_bf16, bp.buf.data(), bp.buf.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    CB2_CUDA(cudaMalloc(&m.dev_f16, bp.buf.size() * sizeof(__half)));
+    CB2_CUDA(cudaMemcpy(m.dev_f16, bp.buf.data(), bp.buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    m.n_f16_blocks = (int)(bp.buf.size() / (128 * 128));
     auto F = [&](const std::string& key) { return (const float*)(m.dev_f32 + off.at(key)); };
-    auto B = [&](const std::string& key) { return (const __nv_bfloat16*)(m.dev_bf16 + boff.at(key)); };
+    auto B = [&](const std::string& key) { return (const __half*)(m.dev_f16 + boff.at(key)); };
     m.freqs = F("freqs"); m.te_w0_t = F("te_w0_t"); m.te_b0 = F("te_b0"); m.te_w2_t = F("te_w2_t"); m.te_b2 = F("te_b2");
     m.ada_w_t = F("ada_w_t"); m.ada_b = F("ada_b"); m.xin_w_t = F("xin_w_t"); m.xin_b = F("xin_b");
     m.pos_table = F("pos_table"); m.wedge_t = F("wedge_t"); m.ln_w = F("ln_w"); m.ln_b = F("ln_b"); m.we_t = F("we_t"); m.we_b = F("we_b");
@@ -264,7 +265,7 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
 void cb2_denoiser_destroy(cb2_denoiser* d) {
     if (!d) return;
     cudaFree(d->m.dev_f32);
-    cudaFree(d->m.dev_bf16);
+    cudaFree(d->m.dev_f16);
     delete d;
 }
 
@@ -361,14 +362,14 @@ void cb2_vae_destroy(cb2_vae* h) {
 // ------------------------------------------------------------------------------------------- plan
 int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, int keep_debug, cb2_plan** out) {
     if (!d || !out || F <= 0 || NB <= 0 || L <= 0) { set_error("plan_create: bad argument"); return 1; }
-    if (precision != PREC_F32 && precision != PREC_BF16) { set_error("plan_create: unknown precision %d", precision); return 1; }
+    if (precision != PREC_F32 && precision != PREC_F16) { set_error("plan_create: unknown precision %d", precision); return 1; }
     cb2_plan* h = new cb2_plan();
     Plan& p = h->p;
     p.model = &d->m; p.F = F; p.NB = NB; p.L = L; p.precision = precision;
     p.K = d->m.k_neighbors < L ? d->m.k_neighbors : L;
     h->keep_debug = keep_debug;
     const size_t N = (size_t)NB * L, FE = (size_t)F * L * p.K, NE = N * p.K;
-    const size_t esz = precision == PREC_BF16 ? 2 : 4;
+    const size_t esz = precision == PREC_F16 ? 2 : 4;
     int e = 0;
     e |= dev_alloc(p.allocs, &p.X, (size_t)F * L * 3);
     e |= dev_alloc(p.allocs, &p.lengths, F);
@@ -382,6 +383,10 @@ int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, 
     e |= dev_alloc(p.allocs, &p.hV, N * 128);
     e |= dev_alloc(p.allocs, &p.hVenc, N * 128);
     e |= dev_alloc(p.allocs, &p.P, 2 * N * 256);
+    if (precision == PREC_F16) {
+        e |= dev_alloc(p.allocs, &p.Pc16[0], N * 128);
+        e |= dev_alloc(p.allocs, &p.Pc16[1], N * 128);
+    }
     e |= dev_alloc(p.allocs, &p.S, N * 128);
     e |= dev_alloc(p.allocs, &p.out6, N * 6);
     e |= dev_alloc(p.allocs, &h->xa, N * 3);
@@ -392,7 +397,7 @@ int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, 
     e |= dev_alloc(p.allocs, &p.tvals, p.mod_capacity);
     e |= dev_alloc(p.allocs, &p.coef, (size_t)p.mod_capacity * 8);
     if (e) { cb2_plan_destroy(h); return e; }
-    if (precision == PREC_BF16) {
+    if (precision == PREC_F16) {
         if (int r = edge_tc_prepare(p)) { cb2_plan_destroy(h); return r; }
     }
     *out = h;
@@ -430,24 +435,32 @@ int cb2_plan_set_frames(cb2_plan* h, const float* X, const int* lengths, const i
 namespace {
 
 int edge_dispatch(Plan& p, int mode, int layer, const float* mod_base, int mod_stride, cudaStream_t s) {
-    return p.precision == PREC_BF16 ? launch_edge_tc(p, mode, layer, mod_base, mod_stride, s)
+    return p.precision == PREC_F16 ? launch_edge_tc(p, mode, layer, mod_base, mod_stride, s)
                                     : launch_edge_f32(p, mode, layer, mod_base, mod_stride, s);
 }
 
 // One denoiser forward; when x_next != nullptr the last kernel also applies the p_sample update.
 int run_forward(Plan& p, const float* x, const float* mod_base, int mod_stride, const float* noise, float* x_next,
-                const float* coef_row, cudaStream_t s) {
+                const float* coef_row, cudaStream_t s, int stop_after = -1) {
+    int n = 0;
+    auto done = [&]() { return stop_after >= 0 && ++n >= stop_after; };     // debug: stop after `stop_after` kernels
     if (int e = launch_node_init(p, x, mod_base, mod_stride, s)) return e;
+    if (done()) return 0;
     for (int l = 0; l < 3; ++l) {
         if (int e = edge_dispatch(p, EDGE_ENC_NODE, l, mod_base, mod_stride, s)) return e;
+        if (done()) return 0;
         if (int e = launch_node_update(p, l, mod_base, mod_stride, nullptr, nullptr, nullptr, nullptr, s)) return e;
+        if (done()) return 0;
         if (int e = edge_dispatch(p, EDGE_ENC_EDGE, l, mod_base, mod_stride, s)) return e;
+        if (done()) return 0;
     }
     for (int l = 0; l < 3; ++l) {
         if (int e = edge_dispatch(p, EDGE_DEC, l, mod_base, mod_stride, s)) return e;
+        if (done()) return 0;
         const bool last = l == 2;
         if (int e = launch_node_update(p, 3 + l, mod_base, mod_stride, last ? x : nullptr, last ? noise : nullptr,
                                        last ? x_next : nullptr, last ? coef_row : nullptr, s)) return e;
+        if (done()) return 0;
     }
     return 0;
 }
@@ -455,6 +468,16 @@ int run_forward(Plan& p, const float* x, const float* mod_base, int mod_stride, 
 }  // namespace
 
 extern "C" {
+
+int cb2_plan_forward_partial(cb2_plan* h, const float* x, const float* t, int stop_after, void* stream) {
+    if (!h || !x || !t) { set_error("forward_partial: null argument"); return 1; }
+    if (!h->frames_ready) { set_error("forward_partial: cb2_plan_set_frames has not been called"); return 1; }
+    Plan& p = h->p;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int e = launch_timestep_mod(*p.model, t, p.NB, p.silu_c, p.mod, s)) return e;
+    p.coef_steps = 0;
+    return run_forward(p, x, p.mod, CB2_MOD_TOTAL, nullptr, nullptr, nullptr, s, stop_after);
+}
 
 int cb2_plan_forward(cb2_plan* h, const float* x, const float* t, float* out, void* stream) {
     if (!h || !x || !t || !out) { set_error("forward: null argument"); return 1; }
@@ -602,7 +625,7 @@ int cb2_plan_buffer(cb2_plan* h, const char* name, void* dst, long long dst_byte
     void** ptr = &src;
     long long* bytes = &size;
     Plan& p = h->p;
-    const size_t N = (size_t)p.NB * p.L, FE = (size_t)p.F * p.L * p.K, esz = p.precision == PREC_BF16 ? 2 : 4;
+    const size_t N = (size_t)p.NB * p.L, FE = (size_t)p.F * p.L * p.K, esz = p.precision == PREC_F16 ? 2 : 4;
     const std::string n = name;
     if (n == "nbr_idx") { *ptr = p.nbr_idx; *bytes = FE * 4; }
     else if (n == "nbr_dist") { *ptr = p.nbr_dist; *bytes = FE * 4; }

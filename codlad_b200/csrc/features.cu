@@ -63,7 +63,7 @@ __device__ __forceinline__ float pair_dist(V3 a, V3 b) {
     return sqrtf(dot(d, d) + 1e-6f);
 }
 
-template <bool OUT_BF16>
+template <bool OUT_F16>
 __global__ void __launch_bounds__(256) edge_features_kernel(
     const float* __restrict__ X, const int* __restrict__ nbr_idx, const float* __restrict__ nbr_dist, int L, int K,
     const float* __restrict__ pos_table, const float* __restrict__ wedge_t, const float* __restrict__ ln_w,
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) edge_features_kernel(
         const int row = row0 + r;
         if (row < K) {
             const float v = acc[r] + bias;
-            if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(hE0)[(node * K + row) * 128 + c] = __float2bfloat16(v);
+            if (OUT_F16) reinterpret_cast<__half*>(hE0)[(node * K + row) * 128 + c] = __float2half_rn(v);
             else reinterpret_cast<float*>(hE0)[(node * K + row) * 128 + c] = v;
         }
     }
@@ -193,7 +193,7 @@ int launch_edge_features(const DenoiserModel& m, const float* X, const int* leng
     }
     const size_t smem = (size_t)(MAXK * RAW_LD + MAXK * 128) * 4 + MAXK * 4 + 16 * 4;
     dim3 grid(L, F);
-    if (precision == PREC_BF16) {
+    if (precision == PREC_F16) {
         CB2_CUDA(cudaFuncSetAttribute(edge_features_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         edge_features_kernel<true><<<grid, 256, smem, s>>>(X, idx, D, L, K, m.pos_table, m.wedge_t, m.ln_w, m.ln_b, m.we_t, m.we_b, E_dbg, hE0);
     } else {

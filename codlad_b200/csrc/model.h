@@ -1,7 +1,7 @@
 // Internal (not part of the C-ABI): packed device-side weights and the per-geometry plan.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <unordered_map>
@@ -12,20 +12,20 @@
 namespace cb2 {
 
 // fp32 weights are stored TRANSPOSED ([in][out]) so that a thread owning output column c reads
-// consecutive addresses across the warp.  bf16 copies keep nn.Linear's [out][in] layout, which is
-// exactly the K-major B operand a tcgen05.mma wants.
+// consecutive addresses across the warp.  fp16 copies keep nn.Linear's [out][in] layout, which is
+// exactly the K-major B operand a tcgen05.mma wants (one 128x128 block per matrix, 128 rows apart).
 struct EncLayerW {
     const float *W1a_t, *W1b_t, *W1c_t, *b1, *W2_t, *b2, *W3_t, *b3;
     const float *W11a_t, *W11b_t, *W11c_t, *b11, *W12_t, *b12, *W13_t, *b13;
     const float *Win_t, *bin, *Wout_t, *bout;
-    const __nv_bfloat16 *W1b_h, *W2_h, *W11b_h, *W12_h, *W13_h;
+    const __half *W1b_h, *W2_h, *W11b_h, *W12_h, *W13_h;
 };
 
 struct DecLayerW {
     // W1 = [W1a | W1b | W1c | W1d] over inputs [h_V_i | 2 h_E | 2 h_S_j | h_V_j + h_Venc_j]
     const float *W1a_t, *W1b2_t /* 2*W1b^T */, *W1d_t, *b1, *TS /* [30][128] = 2 * W_s @ W1c^T */;
     const float *W2_t, *b2, *W3_t, *b3, *Win_t, *bin, *Wout_t, *bout;
-    const __nv_bfloat16 *W1b2_h, *W2_h;
+    const __half *W1b2_h, *W2_h;
 };
 
 struct DenoiserModel {
@@ -40,10 +40,11 @@ struct DenoiserModel {
     DecLayerW dec[3];
     const float *fin_w_t /* [128][6] */, *fin_b;
     float* dev_f32 = nullptr;
-    __nv_bfloat16* dev_bf16 = nullptr;
+    __half* dev_f16 = nullptr;
+    int n_f16_blocks = 0;
 };
 
-enum Precision { PREC_F32 = 0, PREC_BF16 = 1 };
+enum Precision { PREC_F32 = 0, PREC_F16 = 1 };
 
 // One plan = one geometry: F frames of padded length L, NB members (member b uses frame
 // frame_of[b]), K neighbours.  Owns every intermediate buffer of the denoiser.
@@ -58,13 +59,15 @@ struct Plan {
     int* frame_of = nullptr;        // [NB]
     int* nbr_idx = nullptr;         // [F, L, K]
     float* nbr_dist = nullptr;      // [F, L, K]
-    void* hE0 = nullptr;            // [F, L, K, 128] fp32 | bf16
+    void* hE0 = nullptr;            // [F, L, K, 128] fp32 | fp16
     float* E_dbg = nullptr;         // optional [F, L, K, 128] (norm_edges output) for parity tests
     // per-member
-    void* hE = nullptr;             // [NB, L, K, 128] fp32 | bf16
+    void* hE = nullptr;             // [NB, L, K, 128] fp32 | fp16
     float* hV = nullptr;            // [NB*L, 128]
     float* hVenc = nullptr;         // [NB*L, 128]
     float* P = nullptr;             // [2][NB*L, 256] per-node halves of the edge MLPs' first layer: [own | gathered]
+    __half* Pc16[2] = {nullptr, nullptr};   // fp16 tier: [NB*L, 128] copy of the gathered half of each P buffer
+    int num_sms = 148;
     float* silu_c = nullptr;        // [mod_capacity, 128] scratch of the timestep embedder
     float* S = nullptr;             // [NB*L, 128]  aggregated messages
     float* out6 = nullptr;          // [NB*L, 6]

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(128) adaln_table_kernel(const float* __restric
 struct Proj {                // P[n] = [Wa h + ba | Wc h' (+ table[z])],  h' = h (+ h_enc)
     const float *Wa_t, *ba, *Wc_t, *table;
     float* out;              // [N, 256]
+    __half* out16;           // fp16 tier: [N, 128] copy of the gathered half (nullptr in the fp32 tier)
     int add_enc;             // 0: h' = h, 1: h' = h + hVenc[n], 2: h' = 2 h (this kernel is producing hVenc)
 };
 
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(128) node_update_kernel(NodeParams p) {
                     v += pj.table[z * 128 + c];
                 }
                 pj.out[(size_t)n * 256 + 128 + c] = v;
+                if (pj.out16 != nullptr) pj.out16[(size_t)n * 128 + c] = __float2half_rn(v);
             }
         }
     }
@@ -357,7 +359,7 @@ int launch_node_init(Plan& p, const float* x, const float* mod_base, int mod_str
     np.do_update = 0;
     np.x = x; np.xin_w_t = m.xin_w_t; np.xin_b = m.xin_b;
     np.n_proj = 1;
-    np.proj[0] = Proj{m.enc[0].W1a_t, m.enc[0].b1, m.enc[0].W1c_t, nullptr, plan_P(p, 0), 0};
+    np.proj[0] = Proj{m.enc[0].W1a_t, m.enc[0].b1, m.enc[0].W1c_t, nullptr, plan_P(p, 0), p.Pc16[0], 0};
     return node_launch(p, np, s);
 }
 
@@ -374,14 +376,14 @@ int launch_node_update(Plan& p, int phase, const float* mod_base, int mod_stride
         np.W3_t = e.W3_t; np.b3 = e.b3; np.Win_t = e.Win_t; np.bin = e.bin; np.Wout_t = e.Wout_t; np.bout = e.bout;
         np.mod = mod_base + CB2_MOD_ENC_OFF(phase);
         np.n_proj = 2;
-        np.proj[0] = Proj{e.W11a_t, e.b11, e.W11c_t, nullptr, plan_P(p, 1), 0};          // this layer's edge update
+        np.proj[0] = Proj{e.W11a_t, e.b11, e.W11c_t, nullptr, plan_P(p, 1), p.Pc16[1], 0};          // this layer's edge update
         if (phase < 2) {
             const EncLayerW& nx = m.enc[phase + 1];
-            np.proj[1] = Proj{nx.W1a_t, nx.b1, nx.W1c_t, nullptr, plan_P(p, 0), 0};        // next layer's node message
+            np.proj[1] = Proj{nx.W1a_t, nx.b1, nx.W1c_t, nullptr, plan_P(p, 0), p.Pc16[0], 0};        // next layer's node message
         } else {
             const DecLayerW& d = m.dec[0];
             np.write_enc = 1;
-            np.proj[1] = Proj{d.W1a_t, d.b1, d.W1d_t, d.TS, plan_P(p, 0), 2};              // h_V + h_Venc = 2 h_V here
+            np.proj[1] = Proj{d.W1a_t, d.b1, d.W1d_t, d.TS, plan_P(p, 0), p.Pc16[0], 2};              // h_V + h_Venc = 2 h_V here
         }
     } else {
         const int l = phase - 3;
@@ -392,7 +394,7 @@ int launch_node_update(Plan& p, int phase, const float* mod_base, int mod_stride
         if (l < 2) {
             const DecLayerW& nx = m.dec[l + 1];
             np.n_proj = 1;
-            np.proj[0] = Proj{nx.W1a_t, nx.b1, nx.W1d_t, nx.TS, plan_P(p, 0), 1};
+            np.proj[0] = Proj{nx.W1a_t, nx.b1, nx.W1d_t, nx.TS, plan_P(p, 0), p.Pc16[0], 1};
         } else {
             np.n_proj = 0;
             np.do_final = 1;

@@ -34,7 +34,7 @@ class DenoiserEngine:
         del keep
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and N is not None:
             N.lib().cb2_denoiser_destroy(self.handle)
             self.handle = None
 
@@ -62,7 +62,7 @@ class VaeEngine:
         del keep
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and N is not None:
             N.lib().cb2_vae_destroy(self.handle)
             self.handle = None
 
@@ -84,7 +84,7 @@ class Plan:
         self._lengths = None
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and N is not None:
             N.lib().cb2_plan_destroy(self.handle)
             self.handle = None
 
@@ -129,6 +129,12 @@ class Plan:
         out = torch.empty(self.NB, self.L, 6, device=self.device, dtype=torch.float32)
         N.check(N.lib().cb2_plan_forward(self.handle, N.dptr(x), N.dptr(t), N.dptr(out), N.stream_ptr()), "forward")
         return out
+
+    def forward_partial(self, x, t, stop_after: int):
+        """Parity helper: run only the first `stop_after` kernels of forward(); read state with buffer()."""
+        x = x.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device, torch.float32).contiguous()
+        N.check(N.lib().cb2_plan_forward_partial(self.handle, N.dptr(x), N.dptr(t), int(stop_after), N.stream_ptr()), "forward_partial")
 
     def set_schedule(self, timestep_map, coef):
         t = torch.as_tensor(np.asarray(timestep_map), dtype=torch.float32).contiguous()

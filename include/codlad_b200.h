@@ -26,7 +26,7 @@ extern "C" {
 
 #define CB2_ABI_VERSION 1
 #define CB2_PRECISION_F32 0   /* fp32 SIMT tier: tracks the fp32 reference to ~1e-6 */
-#define CB2_PRECISION_BF16 1  /* tcgen05 tier: bf16 operands / edge state, fp32 accumulation */
+#define CB2_PRECISION_F16 1   /* tcgen05 tier: fp16 operands / edge state, fp32 accumulation in TMEM */
 #define CB2_MOD_WIDTH 6016    /* adaLN table row: 3*1152 (enc) + 3*768 (dec) + 256 (final) */
 
 typedef struct cb2_denoiser cb2_denoiser;   /* packed weights of ProteinMPNN_diffusion_new */
@@ -75,6 +75,11 @@ CB2_API int cb2_plan_set_frames(cb2_plan* p, const float* X, const int* lengths,
 /* Replaces: ProteinMPNN_diffusion_new.forward (models/latent_model.py:175-268) for the geometry set above.
  * x [NB,L,3], t [NB] fp32 timesteps (already mapped to the original 0..999 scale) -> out [NB,L,6]. */
 CB2_API int cb2_plan_forward(cb2_plan* p, const float* x, const float* t, float* out, void* stream);
+
+/* Debug / parity: the first `stop_after` kernels of cb2_plan_forward (1 = node init, then per encoder layer
+ * node-message, node-update, edge-update; then per decoder layer message, node-update); inspect the state with
+ * cb2_plan_buffer. */
+CB2_API int cb2_plan_forward_partial(cb2_plan* p, const float* x, const float* t, int stop_after, void* stream);
 
 /* Replaces: SpacedDiffusion/GaussianDiffusion coefficient tables + _WrappedModel timestep remap
  * (diffusion_and_flow/respace.py:73-129, gaussian_diffusion.py:175-209).  HOST arrays: t_of_step [T] =
