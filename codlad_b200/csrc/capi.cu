@@ -198,6 +198,11 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         off[k + "Wout_t"] = pk.transposed(wout, H, 4 * H, 0, 4 * H); off[k + "bout"] = pk.copy(bout, H);
         boff[k + "W1b"] = bp.block(w1, 3 * H, H); boff[k + "W2"] = bp.block(w2, H, 0);
         boff[k + "W11b"] = bp.block(w11, 3 * H, H); boff[k + "W12"] = bp.block(w12, H, 0); boff[k + "W13"] = bp.block(w13, H, 0);
+        boff[k + "W1a"] = bp.block(w1, 3 * H, 0); boff[k + "W1c"] = bp.block(w1, 3 * H, 2 * H);
+        boff[k + "W11a"] = bp.block(w11, 3 * H, 0); boff[k + "W11c"] = bp.block(w11, 3 * H, 2 * H);
+        boff[k + "W3"] = bp.block(w3, H, 0);
+        for (int q = 0; q < 4; ++q) { size_t o = bp.block(win + (size_t)q * H * H, H, 0); if (q == 0) boff[k + "Win"] = o; }
+        for (int q = 0; q < 4; ++q) { size_t o = bp.block(wout, 4 * H, q * H); if (q == 0) boff[k + "Wout"] = o; }
     }
     for (int l = 0; l < 3; ++l) {
         const std::string p = "decoder_layers." + std::to_string(l), k = "d" + std::to_string(l) + ".";
@@ -222,6 +227,10 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         off[k + "Win_t"] = pk.transposed(win, 4 * H, H, 0, H); off[k + "bin"] = pk.copy(bin, 4 * H);
         off[k + "Wout_t"] = pk.transposed(wout, H, 4 * H, 0, 4 * H); off[k + "bout"] = pk.copy(bout, H);
         boff[k + "W1b2"] = bp.block(w1, 4 * H, H, 2.0f); boff[k + "W2"] = bp.block(w2, H, 0);
+        boff[k + "W1a"] = bp.block(w1, 4 * H, 0); boff[k + "W1d"] = bp.block(w1, 4 * H, 3 * H);
+        boff[k + "W3"] = bp.block(w3, H, 0);
+        for (int q = 0; q < 4; ++q) { size_t o = bp.block(win + (size_t)q * H * H, H, 0); if (q == 0) boff[k + "Win"] = o; }
+        for (int q = 0; q < 4; ++q) { size_t o = bp.block(wout, 4 * H, q * H); if (q == 0) boff[k + "Wout"] = o; }
     }
     GET(finw, "W_out.linear.weight", 6 * H) GET(finb, "W_out.linear.bias", 6)
     off["fin_w_t"] = pk.transposed(finw, 6, H, 0, H); off["fin_b"] = pk.copy(finb, 6);
@@ -248,6 +257,8 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         e.W12_t = F(k + "W12_t"); e.b12 = F(k + "b12"); e.W13_t = F(k + "W13_t"); e.b13 = F(k + "b13");
         e.Win_t = F(k + "Win_t"); e.bin = F(k + "bin"); e.Wout_t = F(k + "Wout_t"); e.bout = F(k + "bout");
         e.W1b_h = B(k + "W1b"); e.W2_h = B(k + "W2"); e.W11b_h = B(k + "W11b"); e.W12_h = B(k + "W12"); e.W13_h = B(k + "W13");
+        e.W1a_h = B(k + "W1a"); e.W1c_h = B(k + "W1c"); e.W11a_h = B(k + "W11a"); e.W11c_h = B(k + "W11c");
+        e.W3_h = B(k + "W3"); e.Win_h = B(k + "Win"); e.Wout_h = B(k + "Wout");
     }
     for (int l = 0; l < 3; ++l) {
         const std::string k = "d" + std::to_string(l) + ".";
@@ -256,6 +267,7 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         e.W2_t = F(k + "W2_t"); e.b2 = F(k + "b2"); e.W3_t = F(k + "W3_t"); e.b3 = F(k + "b3");
         e.Win_t = F(k + "Win_t"); e.bin = F(k + "bin"); e.Wout_t = F(k + "Wout_t"); e.bout = F(k + "bout");
         e.W1b2_h = B(k + "W1b2"); e.W2_h = B(k + "W2");
+        e.W1a_h = B(k + "W1a"); e.W1d_h = B(k + "W1d"); e.W3_h = B(k + "W3"); e.Win_h = B(k + "Win"); e.Wout_h = B(k + "Wout");
     }
     m.fin_w_t = F("fin_w_t"); m.fin_b = F("fin_b");
     *out = d;
@@ -399,6 +411,7 @@ int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, 
     if (e) { cb2_plan_destroy(h); return e; }
     if (precision == PREC_F16) {
         if (int r = edge_tc_prepare(p)) { cb2_plan_destroy(h); return r; }
+        if (int r = node_tc_prepare(p)) { cb2_plan_destroy(h); return r; }
     }
     *out = h;
     return 0;
@@ -408,6 +421,7 @@ void cb2_plan_destroy(cb2_plan* h) {
     if (!h) return;
     if (h->p.graph) cudaGraphExecDestroy(h->p.graph);
     edge_tc_release(h->p);
+    node_tc_release(h->p);
     for (void* q : h->p.allocs) cudaFree(q);
     delete h;
 }
@@ -444,12 +458,17 @@ int run_forward(Plan& p, const float* x, const float* mod_base, int mod_stride, 
                 const float* coef_row, cudaStream_t s, int stop_after = -1) {
     int n = 0;
     auto done = [&]() { return stop_after >= 0 && ++n >= stop_after; };     // debug: stop after `stop_after` kernels
-    if (int e = launch_node_init(p, x, mod_base, mod_stride, s)) return e;
+    const bool tc = p.precision == PREC_F16 && p.node_tc != nullptr;
+    auto node_update = [&](int phase, const float* xt, const float* nz, float* xn, const float* cf) {
+        return tc ? launch_node_update_tc(p, phase, mod_base, mod_stride, xt, nz, xn, cf, s)
+                  : launch_node_update(p, phase, mod_base, mod_stride, xt, nz, xn, cf, s);
+    };
+    if (int e = tc ? launch_node_init_tc(p, x, s) : launch_node_init(p, x, mod_base, mod_stride, s)) return e;
     if (done()) return 0;
     for (int l = 0; l < 3; ++l) {
         if (int e = edge_dispatch(p, EDGE_ENC_NODE, l, mod_base, mod_stride, s)) return e;
         if (done()) return 0;
-        if (int e = launch_node_update(p, l, mod_base, mod_stride, nullptr, nullptr, nullptr, nullptr, s)) return e;
+        if (int e = node_update(l, nullptr, nullptr, nullptr, nullptr)) return e;
         if (done()) return 0;
         if (int e = edge_dispatch(p, EDGE_ENC_EDGE, l, mod_base, mod_stride, s)) return e;
         if (done()) return 0;
@@ -458,8 +477,7 @@ int run_forward(Plan& p, const float* x, const float* mod_base, int mod_stride, 
         if (int e = edge_dispatch(p, EDGE_DEC, l, mod_base, mod_stride, s)) return e;
         if (done()) return 0;
         const bool last = l == 2;
-        if (int e = launch_node_update(p, 3 + l, mod_base, mod_stride, last ? x : nullptr, last ? noise : nullptr,
-                                       last ? x_next : nullptr, last ? coef_row : nullptr, s)) return e;
+        if (int e = node_update(3 + l, last ? x : nullptr, last ? noise : nullptr, last ? x_next : nullptr, last ? coef_row : nullptr)) return e;
         if (done()) return 0;
     }
     return 0;

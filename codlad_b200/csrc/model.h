@@ -19,6 +19,7 @@ struct EncLayerW {
     const float *W11a_t, *W11b_t, *W11c_t, *b11, *W12_t, *b12, *W13_t, *b13;
     const float *Win_t, *bin, *Wout_t, *bout;
     const __half *W1b_h, *W2_h, *W11b_h, *W12_h, *W13_h;
+    const __half *W1a_h, *W1c_h, *W11a_h, *W11c_h, *W3_h, *Win_h /* 4 blocks */, *Wout_h /* 4 blocks */;
 };
 
 struct DecLayerW {
@@ -26,6 +27,7 @@ struct DecLayerW {
     const float *W1a_t, *W1b2_t /* 2*W1b^T */, *W1d_t, *b1, *TS /* [30][128] = 2 * W_s @ W1c^T */;
     const float *W2_t, *b2, *W3_t, *b3, *Win_t, *bin, *Wout_t, *bout;
     const __half *W1b2_h, *W2_h;
+    const __half *W1a_h, *W1d_h, *W3_h, *Win_h /* 4 blocks */, *Wout_h /* 4 blocks */;
 };
 
 struct DenoiserModel {
@@ -82,7 +84,8 @@ struct Plan {
     const void* graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
     int graph_steps = 0;
     std::vector<void*> allocs;
-    void* tmaps = nullptr;          // device/host-side CUtensorMap storage for the tcgen05 path
+    void* tmaps = nullptr;          // host-side CUtensorMap storage of the tcgen05 edge kernels
+    void* node_tc = nullptr;        // ... and of the tcgen05 node kernels
     long long launches = 0;         // kernels launched through this plan (bench: gpu_launches)
 };
 
@@ -102,6 +105,11 @@ int launch_node_update(Plan& p, int phase /*0..2 enc, 3..5 dec*/, const float* m
 int launch_edge_f32(Plan& p, int mode, int layer, const float* mod_base, int mod_stride_b, cudaStream_t s);
 int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_stride_b, cudaStream_t s);
 int edge_tc_prepare(Plan& p);
+int node_tc_prepare(Plan& p);
+void node_tc_release(Plan& p);
+int launch_node_init_tc(Plan& p, const float* x, cudaStream_t s);
+int launch_node_update_tc(Plan& p, int phase, const float* mod_base, int mod_stride_b, const float* x_t, const float* noise,
+                          float* x_next, const float* coef_row, cudaStream_t s);
 void edge_tc_release(Plan& p);
 
 enum EdgeMode { EDGE_ENC_NODE = 0, EDGE_ENC_EDGE = 1, EDGE_DEC = 2 };
