@@ -54,20 +54,52 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <int NWG>
+// packed-half helpers of the epilogues
+__device__ __forceinline__ uint32_t pack_sat(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// erf-GELU ~= 0.5 x (1 + tanh(x (a + b x^2))) on two fp16 values (coefficients refitted, see gelu_fast)
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+    const __half2 x2 = __hmul2(x, x);
+    const __half2 pl = __hfma2(x2, __float2half2_rn(0.03470094f), __float2half2_rn(0.80015698f));
+    const __half2 u = __hmul2(x, pl);
+    uint32_t t;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(as_u32(u)));
+    const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
+    return __hfma2(h, as_h2(t), h);
+}
+
+struct TileMeta {
+    int b, i0, nv;
+    int in_row0, out_row0;
+    size_t node0;
+    bool row_valid, row_on;
+    int q_of_r;
+    const __half* pc_row;
+    float pa[MAX_NPT];
+    float modA, modB;        // ENC_EDGE: gate (1 + scale) and gate * shift of this thread's column
+};
+
+template <int NWG, int MODE>
 __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms repeat every 1 KiB
-    // layout: [weights n_w x 32 KB][tiles NWG x 32 KB][indicator 4 KB][per-WG scratch]
+    // layout: [weights n_w x 32 KB][tiles NWG x 32 KB][indicator 4 KB][CTA vectors][per-WG vectors][barriers]
     unsigned char* sW = smem;
     unsigned char* sT = sW + p.n_w * TILE_BYTES;
     unsigned char* sInd = sT + NWG * TILE_BYTES;
-    float* sVec = reinterpret_cast<float*>(sInd + IND_BYTES);            // per WG: [MAX_NPT + 5][128] floats
-    constexpr int VEC_PER_WG = (MAX_NPT + 5) * 128;
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sVec + NWG * VEC_PER_WG);   // [0] weights, [1 + 2 wg] load, [2 + 2 wg] mma
+    __half* sB2h = reinterpret_cast<__half*>(sInd + IND_BYTES);          // [128] second-layer bias, fp16
+    float* sB3 = reinterpret_cast<float*>(sB2h + 128);                   // [128] third-layer bias, fp32
+    __half* sWgVec = reinterpret_cast<__half*>(sB3 + 128);               // per WG: Pa[MAX_NPT][128], modA[128], modB[128]
+    constexpr int VEC_PER_WG = (MAX_NPT + 2) * 128;
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sWgVec + NWG * VEC_PER_WG);   // [0] weights, [1 + 2 wg] load, [2 + 2 wg] mma
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1 + 2 * NWG);
 
-    const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp_in_wg = wt >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp_in_wg = wt >> 5;
     const int K = p.K, NPT = p.NPT;
 
     // ---- one-time setup: barriers, TMEM, weights, indicator operand ----
@@ -94,6 +126,10 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_cons
         const uint32_t off = (uint32_t)((c16 >> 3) * (16 * 128) + q * 128 + (((c16 & 7) ^ (q & 7)) << 4));
         *reinterpret_cast<uint4*>(sInd + off) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if (tid < 128) {
+        sB2h[tid] = __float2half_rn(p.b2[tid]);
+        sB3[tid] = MODE == EDGE_ENC_EDGE ? p.b3[tid] : 0.f;
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -108,12 +144,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_cons
 
     unsigned char* T = sT + wg * TILE_BYTES;
     const uint32_t T_u32 = smem_u32(T);
-    float* vec = sVec + wg * VEC_PER_WG;      // [0..NPT) Pa rows, then b2, b3, shift, scale, gate
-    float* vB2 = vec + MAX_NPT * 128;
-    float* vB3 = vB2 + 128;
-    float* vShift = vB3 + 128;
-    float* vScale = vShift + 128;
-    float* vGate = vScale + 128;
+    __half* sPa = sWgVec + wg * VEC_PER_WG;
+    __half* sModA = sPa + MAX_NPT * 128;
+    __half* sModB = sModA + 128;
     const uint32_t bar_load = smem_u32(&sBar[1 + 2 * wg]), bar_mma = smem_u32(&sBar[2 + 2 * wg]);
     const uint32_t tmem_acc = tmem_base + (uint32_t)(wg * 128);                       // this pipeline's 128 accumulator columns
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(warp_in_wg * 32) << 16);         // + this warp's lane quarter
@@ -122,83 +155,109 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_cons
     constexpr uint32_t IDESC_RED = umma_idesc(128, 16, 1, 0);
     uint32_t ph_load = 0, ph_mma = 0;
     bool weights_ready = false;
-
-    // second/third layer biases are tile-invariant
-    vB2[wt] = p.b2[wt];
-    if (p.mode == EDGE_ENC_EDGE) vB3[wt] = p.b3[wt];
-
     const int r = wt;                          // this thread's tile row == TMEM lane
-    for (int tile = blockIdx.x * NWG + wg; tile < p.n_tiles; tile += gridDim.x * NWG) {
-        const int b = tile / p.tiles_per_member;
-        const int i0 = (tile - b * p.tiles_per_member) * NPT;
-        const int nv = min(NPT, p.L - i0);                     // valid nodes in this tile
-        const int f = p.frame_of[b];
-        const int len = p.lengths[f];
-        const size_t node0 = (size_t)b * p.L + i0;             // first node (member indexing)
-        const int in_row0 = (int)(((size_t)(p.in_is_frame ? f : b) * p.L + i0) * K);
-        const int out_row0 = (int)(node0 * K);
+    const int tile_stride = gridDim.x * NWG;
 
-        // ---- (1) TMA load of the h_E rows (one box per node and 64-column half) ----
-        if (wt == 0) {
-            if (p.mode == EDGE_ENC_EDGE) tma_store_wait_read();          // previous tile's store has finished reading T
-            mbar_expect_tx(bar_load, (uint32_t)(nv * K * 256));
-            for (int q = 0; q < nv; ++q)
-                for (int h = 0; h < 2; ++h)
-                    tma_load_2d(T_u32 + h * HALF_BYTES + q * K * 128, in_map, h * 64, in_row0 + q * K, bar_load);
-        }
-        // ---- per-row metadata and per-tile vectors (overlaps the TMA) ----
-        const int q_of_r = r / K;
-        const bool row_valid = q_of_r < nv;
+    // per-tile metadata: every global load it needs is issued one tile ahead
+    auto load_meta = [&](int tile) {
+        TileMeta m;
+        m.b = tile / p.tiles_per_member;
+        m.i0 = (tile - m.b * p.tiles_per_member) * NPT;
+        m.nv = min(NPT, p.L - m.i0);
+        const int f = p.frame_of[m.b];
+        const int len = p.lengths[f];
+        m.node0 = (size_t)m.b * p.L + m.i0;
+        m.in_row0 = (int)(((size_t)(p.in_is_frame ? f : m.b) * p.L + m.i0) * K);
+        m.out_row0 = (int)(m.node0 * K);
+        m.q_of_r = r / K;
+        m.row_valid = m.q_of_r < m.nv;
         int j = 0;
-        bool row_on = false;
-        if (row_valid) {
-            const int i = i0 + q_of_r;
-            j = p.nbr_idx[((size_t)f * p.L + i) * K + (r - q_of_r * K)];
-            row_on = (p.mode == EDGE_DEC) ? true : (i < len && j < len);
+        m.row_on = false;
+        if (m.row_valid) {
+            const int i = m.i0 + m.q_of_r;
+            j = p.nbr_idx[((size_t)f * p.L + i) * K + (r - m.q_of_r * K)];
+            m.row_on = (MODE == EDGE_DEC) ? true : (i < len && j < len);
         }
-        const __half* pc_row = p.Pc + ((size_t)b * p.L + j) * 128;
-        for (int q = 0; q < nv; ++q) vec[q * 128 + wt] = p.P[(node0 + q) * 256 + wt];
-        if (p.mode == EDGE_ENC_EDGE) {
-            const float* m = p.mod + (size_t)b * p.mod_stride;
-            vShift[wt] = m[768 + wt]; vScale[wt] = 1.0f + m[896 + wt]; vGate[wt] = m[1024 + wt];
+        m.pc_row = p.Pc + ((size_t)m.b * p.L + j) * 128;
+#pragma unroll
+        for (int q = 0; q < MAX_NPT; ++q) m.pa[q] = q < m.nv ? p.P[(m.node0 + q) * 256 + wt] : 0.f;
+        m.modA = 0.f; m.modB = 0.f;
+        if (MODE == EDGE_ENC_EDGE) {
+            const float* md = p.mod + (size_t)m.b * p.mod_stride;
+            const float gate = md[1024 + wt];
+            m.modA = gate * (1.0f + md[896 + wt]);
+            m.modB = gate * md[768 + wt];
         }
+        return m;
+    };
+    auto issue_load = [&](const TileMeta& m) {          // one thread: TMA of the tile's h_E rows, one box per node and half
+        mbar_expect_tx(bar_load, (uint32_t)(m.nv * K * 256));
+        for (int q = 0; q < m.nv; ++q)
+            for (int h = 0; h < 2; ++h)
+                tma_load_2d(T_u32 + h * HALF_BYTES + q * K * 128, in_map, h * 64, m.in_row0 + q * K, bar_load);
+    };
+    auto issue_mma = [&](int w_slot) {                  // one thread: 128x128x128 GEMM, A = activation tile, B = weight slot
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
+            umma_f16(tmem_acc, umma_desc(T_u32 + koff, 16, 1024), umma_desc(smem_u32(sW + w_slot * TILE_BYTES) + koff, 16, 1024), IDESC_MAIN, k > 0);
+        }
+        umma_commit(bar_mma);
+    };
+
+    int tile = blockIdx.x * NWG + wg;
+    TileMeta nxt{};
+    if (tile < p.n_tiles) {
+        nxt = load_meta(tile);
+        if (wt == 0) issue_load(nxt);
+    }
+    while (tile < p.n_tiles) {
+        const TileMeta cur = nxt;
+        const int next_tile = tile + tile_stride;
+        // ---- stage this tile's per-node / per-member vectors ----
+#pragma unroll
+        for (int q = 0; q < MAX_NPT; ++q) sPa[q * 128 + wt] = __float2half_rn(cur.pa[q]);
+        if (MODE == EDGE_ENC_EDGE) { sModA[wt] = __float2half_rn(cur.modA); sModB[wt] = __float2half_rn(cur.modB); }
         wg_sync(wg);
         if (!weights_ready) { mbar_wait(smem_u32(&sBar[0]), 0); weights_ready = true; }
+        uint32_t pc0[16], pc1[16];                       // gathered Pc[j] chunks (32 halves each), double buffered
+        {
+            uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pc0[0]);
+            uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pc0[8]);
+            ldg256(cur.pc_row, lo); ldg256(cur.pc_row + 16, hi);
+        }
         mbar_wait(bar_load, ph_load); ph_load ^= 1;
 
-        // ---- (2) MMA 1: acc = h_E . W?b^T ----
-        if (wt == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-                umma_f16(tmem_acc, umma_desc(T_u32 + koff, 16, 1024), umma_desc(smem_u32(sW) + koff, 16, 1024), IDESC_MAIN, k > 0);
-            }
-            umma_commit(bar_mma);
-        }
+        // ---- MMA 1: acc = h_E . W?b^T ; then prefetch the next tile's metadata while it runs ----
+        if (wt == 0) issue_mma(0);
+        if (next_tile < p.n_tiles) nxt = load_meta(next_tile);
         mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
         tc_fence_after();
 
-        // ---- (3) epilogue 1: + Pa[i] + Pc[j], GELU -> fp16 activation tile ----
+        // ---- epilogue 1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile (packed-half arithmetic) ----
         {
-            const float* pa = vec + (row_valid ? q_of_r : 0) * 128;
-#pragma unroll 1
+            const __half* pa_row = sPa + (cur.row_valid ? cur.q_of_r : 0) * 128;
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
+                uint32_t (&pcc)[16] = (c & 1) ? pc1 : pc0;
+                uint32_t (&pcn)[16] = (c & 1) ? pc0 : pc1;
+                if (c < 3) {
+                    uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pcn[0]);
+                    uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pcn[8]);
+                    ldg256(cur.pc_row + (c + 1) * 32, lo); ldg256(cur.pc_row + (c + 1) * 32 + 16, hi);
+                }
                 float acc[32];
-                uint32_t g0[8], g1[8];
-                ldg256(pc_row + c * 32, g0);
-                ldg256(pc_row + c * 32 + 16, g1);
                 tmem_ld32(tmem_row + c * 32, acc);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    const uint4 pav = *reinterpret_cast<const uint4*>(pa_row + c * 32 + u * 8);
+                    const uint32_t pa4[4] = {pav.x, pav.y, pav.z, pav.w};
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int col = u * 8 + e * 2;
-                        const uint32_t gp = (u < 2) ? g0[u * 4 + e] : g1[(u - 2) * 4 + e];
-                        const float2 pc = h2_to_f2(gp);
-                        const float2 pav = *reinterpret_cast<const float2*>(pa + c * 32 + col);
-                        o[e] = f2_to_h2(gelu_fast((acc[col] + pav.x) + pc.x), gelu_fast((acc[col + 1] + pav.y) + pc.y));
+                        const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(pa4[e])), as_h2(pcc[u * 4 + e]));
+                        o[e] = as_u32(gelu_h2(x));
                     }
                     *reinterpret_cast<uint4*>(T + tile_off(r, c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -208,34 +267,27 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_cons
         tc_fence_before();
         wg_sync(wg);
 
-        // ---- (4) MMA 2 ----
-        if (wt == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-                umma_f16(tmem_acc, umma_desc(T_u32 + koff, 16, 1024), umma_desc(smem_u32(sW + TILE_BYTES) + koff, 16, 1024), IDESC_MAIN, k > 0);
-            }
-            umma_commit(bar_mma);
-        }
+        // ---- MMA 2 ----
+        if (wt == 0) issue_mma(1);
         mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
         tc_fence_after();
 
-        // ---- (5) epilogue 2: + b2, GELU (masked rows -> 0 for the reduction) -> fp16 tile ----
+        // ---- epilogue 2: GELU(acc + b2) (masked rows -> 0 for the reduction) -> fp16 tile ----
         {
-            const bool keep = (p.mode == EDGE_ENC_EDGE) ? true : row_on;
-#pragma unroll 1
+            const uint32_t keep = (MODE == EDGE_ENC_EDGE || cur.row_on) ? 0xffffffffu : 0u;     // bit mask: no branch per pair
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float acc[32];
                 tmem_ld32(tmem_row + c * 32, acc);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    const uint4 bv = *reinterpret_cast<const uint4*>(sB2h + c * 32 + u * 8);
+                    const uint32_t b4[4] = {bv.x, bv.y, bv.z, bv.w};
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int col = u * 8 + e * 2;
-                        const float2 bb = *reinterpret_cast<const float2*>(vB2 + c * 32 + col);
-                        o[e] = keep ? f2_to_h2(gelu_fast(acc[col] + bb.x), gelu_fast(acc[col + 1] + bb.y)) : 0u;
+                        const __half2 x = __hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(b4[e]));
+                        o[e] = as_u32(gelu_h2(x)) & keep;
                     }
                     *reinterpret_cast<uint4*>(T + tile_off(r, c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
@@ -245,8 +297,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_cons
         tc_fence_before();
         wg_sync(wg);
 
-        if (p.mode != EDGE_ENC_EDGE) {
-            // ---- (6a) neighbour sum as an MMA: D[c, q] = sum_r G[r, c] Ind[q, r]  (A = G^T, MN-major view of the tile) ----
+        if (MODE != EDGE_ENC_EDGE) {
+            // ---- neighbour sum as an MMA: D[c, q] = sum_r G[r, c] Ind[q, r]  (A = G^T, MN-major view of the tile) ----
             if (wt == 0) {
                 tc_fence_after();
 #pragma unroll
@@ -259,91 +311,97 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_cons
             }
             mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
             tc_fence_after();
+            if (wt == 0 && next_tile < p.n_tiles) issue_load(nxt);       // T is free: start the next tile's TMA now
             float s4[4];
             tmem_ld4(tmem_row, s4);             // lane = output column, 4 columns = nodes of the tile
 #pragma unroll
             for (int q = 0; q < MAX_NPT; ++q)
-                if (q < nv) p.S[(node0 + q) * 128 + wt] = s4[q];
+                if (q < cur.nv) p.S[(cur.node0 + q) * 128 + wt] = s4[q];
             tc_fence_before();
-            wg_sync(wg);                        // TMEM / T / vec are reused by the next tile
+            wg_sync(wg);                        // TMEM and the per-tile vectors are reused by the next tile
         } else {
-            // ---- (6b) MMA 3 (W13), then residual + LayerNorm + adaLN -> fp16 tile -> TMA store ----
-            if (wt == 0) {
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-                    umma_f16(tmem_acc, umma_desc(T_u32 + koff, 16, 1024), umma_desc(smem_u32(sW + 2 * TILE_BYTES) + koff, 16, 1024), IDESC_MAIN, k > 0);
-                }
-                umma_commit(bar_mma);
+            // ---- MMA 3 (W13), then residual + LayerNorm + adaLN -> fp16 tile -> TMA store ----
+            const __half* res_row = p.res + ((size_t)cur.in_row0 + (cur.row_valid ? r : 0)) * 128;
+            uint32_t rs0[16], rs1[16];
+            {
+                uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rs0[0]);
+                uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rs0[8]);
+                ldg256_coherent(res_row, lo); ldg256_coherent(res_row + 16, hi);
             }
+            if (wt == 0) issue_mma(2);
             mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
             tc_fence_after();
-            const __half* res_row = p.res + ((size_t)in_row0 + (row_valid ? r : 0)) * 128;
+            // pass A (fp32): v = residual + acc + b13, row statistics; v is parked as fp16 in this thread's tile row
             float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float acc[32];
-                uint32_t g0[8], g1[8];
-                ldg256_coherent(res_row + c * 32, g0);
-                ldg256_coherent(res_row + c * 32 + 16, g1);
-                tmem_ld32(tmem_row + c * 32, acc);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float2 rr = h2_to_f2(e < 8 ? g0[e] : g1[e - 8]);
-                    const float2 bb = *reinterpret_cast<const float2*>(vB3 + c * 32 + e * 2);
-                    const float v0 = rr.x + (acc[e * 2] + bb.x), v1 = rr.y + (acc[e * 2 + 1] + bb.y);
-                    sum += v0 + v1;
-                    sq = fmaf(v0, v0, fmaf(v1, v1, sq));
-                }
-            }
-            const float mean = sum * (1.0f / 128.0f);
-            const float var = fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + 1e-6f);
-            const float nmr = -mean * rstd;
-#pragma unroll 1
             for (int c = 0; c < 4; ++c) {
+                uint32_t (&rc)[16] = (c & 1) ? rs1 : rs0;
+                uint32_t (&rn)[16] = (c & 1) ? rs0 : rs1;
+                if (c < 3) {
+                    uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rn[0]);
+                    uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rn[8]);
+                    ldg256_coherent(res_row + (c + 1) * 32, lo); ldg256_coherent(res_row + (c + 1) * 32 + 16, hi);
+                }
                 float acc[32];
-                uint32_t g0[8], g1[8];
-                ldg256_coherent(res_row + c * 32, g0);
-                ldg256_coherent(res_row + c * 32 + 16, g1);
                 tmem_ld32(tmem_row + c * 32, acc);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int col = u * 8 + e * 2, gi = u * 4 + e;
-                        const float2 rr = h2_to_f2(gi < 8 ? g0[gi] : g1[gi - 8]);
-                        const float2 bb = *reinterpret_cast<const float2*>(vB3 + c * 32 + col);
-                        const float2 sh = *reinterpret_cast<const float2*>(vShift + c * 32 + col);
-                        const float2 sc = *reinterpret_cast<const float2*>(vScale + c * 32 + col);
-                        const float2 gt = *reinterpret_cast<const float2*>(vGate + c * 32 + col);
+                        const int col = u * 8 + e * 2;
+                        const float2 rr = h2_to_f2(rc[u * 4 + e]);
+                        const float2 bb = *reinterpret_cast<const float2*>(sB3 + c * 32 + col);
                         const float v0 = rr.x + (acc[col] + bb.x), v1 = rr.y + (acc[col + 1] + bb.y);
-                        o[e] = f2_to_h2(gt.x * fmaf(fmaf(v0, rstd, nmr), sc.x, sh.x), gt.y * fmaf(fmaf(v1, rstd, nmr), sc.y, sh.y));
+                        sum += v0 + v1;
+                        sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+                        o[e] = pack_sat(v0, v1);
                     }
                     *reinterpret_cast<uint4*>(T + tile_off(r, c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+            }
+            const float mean = sum * (1.0f / 128.0f);
+            const float var = fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f);
+            const __half2 rstd2 = __float2half2_rn(rsqrtf(var + 1e-6f));
+            const __half2 mean2 = __float2half2_rn(mean);
+            // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
+#pragma unroll
+            for (int c16 = 0; c16 < 16; ++c16) {
+                uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, c16));
+                const uint4 vv = *slot;
+                const uint4 av = *reinterpret_cast<const uint4*>(sModA + c16 * 8);
+                const uint4 bv = *reinterpret_cast<const uint4*>(sModB + c16 * 8);
+                const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w}, a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
+                *slot = make_uint4(o[0], o[1], o[2], o[3]);
             }
             fence_async_smem();
             tc_fence_before();
             wg_sync(wg);
             if (wt == 0) {
-                for (int q = 0; q < nv; ++q)
+                for (int q = 0; q < cur.nv; ++q)
                     for (int h = 0; h < 2; ++h)
-                        tma_store_2d(&maps.state, h * 64, out_row0 + q * K, T_u32 + h * HALF_BYTES + q * K * 128);
+                        tma_store_2d(&maps.state, h * 64, cur.out_row0 + q * K, T_u32 + h * HALF_BYTES + q * K * 128);
                 tma_store_commit();
+                if (next_tile < p.n_tiles) {
+                    tma_store_wait_read();                               // the store has finished reading T
+                    issue_load(nxt);
+                }
             }
         }
+        tile = next_tile;
     }
-    if (p.mode == EDGE_ENC_EDGE && wt == 0) tma_store_wait_all();
+    if (MODE == EDGE_ENC_EDGE && wt == 0) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 size_t tc_smem_bytes(int nwg, int n_w) {
-    return (size_t)n_w * TILE_BYTES + (size_t)nwg * TILE_BYTES + IND_BYTES + (size_t)nwg * (MAX_NPT + 5) * 128 * 4 +
+    return (size_t)n_w * TILE_BYTES + (size_t)nwg * TILE_BYTES + IND_BYTES + 128 * 2 + 128 * 4 + (size_t)nwg * (MAX_NPT + 2) * 128 * 2 +
            (1 + 2 * nwg) * 8 + 16 + 1024 /* alignment slack */;
 }
 
@@ -361,8 +419,9 @@ int edge_tc_prepare(Plan& p) {
     int dev = 0;
     CB2_CUDA(cudaGetDevice(&dev));
     CB2_CUDA(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4, 2)));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(3, 3)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<4, EDGE_ENC_NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4, 2)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<4, EDGE_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4, 2)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<3, EDGE_ENC_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(3, 3)));
     return 0;
 }
 
@@ -403,10 +462,11 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     }
     if (mode == EDGE_ENC_EDGE) {
         const int grid = min(p.num_sms, (tp.n_tiles + 2) / 3);
-        edge_tc_kernel<3><<<grid, 3 * 128, tc_smem_bytes(3, 3), s>>>(maps, tp);
+        edge_tc_kernel<3, EDGE_ENC_EDGE><<<grid, 3 * 128, tc_smem_bytes(3, 3), s>>>(maps, tp);
     } else {
         const int grid = min(p.num_sms, (tp.n_tiles + 3) / 4);
-        edge_tc_kernel<4><<<grid, 4 * 128, tc_smem_bytes(4, 2), s>>>(maps, tp);
+        if (mode == EDGE_ENC_NODE) edge_tc_kernel<4, EDGE_ENC_NODE><<<grid, 4 * 128, tc_smem_bytes(4, 2), s>>>(maps, tp);
+        else edge_tc_kernel<4, EDGE_DEC><<<grid, 4 * 128, tc_smem_bytes(4, 2), s>>>(maps, tp);
     }
     CB2_LAUNCH_CHECK();
     p.launches++;
