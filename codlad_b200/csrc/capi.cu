@@ -240,6 +240,27 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
     m.k_neighbors = k_neighbors;
     CB2_CUDA(cudaMalloc(&m.dev_f32, pk.buf.size() * sizeof(float)));
     CB2_CUDA(cudaMemcpy(m.dev_f32, pk.buf.data(), pk.buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        std::vector<__half> v16;
+        std::map<std::string, size_t> voff;
+        auto putv = [&](const std::string& key, const float* src) {
+            voff[key] = v16.size();
+            for (int q = 0; q < H; ++q) v16.push_back(__float2half_rn(src[q]));
+        };
+        for (int l = 0; l < 3; ++l) {
+            const std::string pe = "encoder_layers." + std::to_string(l), pd = "decoder_layers." + std::to_string(l);
+            putv("e" + std::to_string(l) + ".b2", tt.get(pe + ".W2.bias", H));
+            putv("e" + std::to_string(l) + ".b12", tt.get(pe + ".W12.bias", H));
+            putv("d" + std::to_string(l) + ".b2", tt.get(pd + ".W2.bias", H));
+        }
+        CB2_CUDA(cudaMalloc(&m.dev_vec16, v16.size() * sizeof(__half)));
+        CB2_CUDA(cudaMemcpy(m.dev_vec16, v16.data(), v16.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        for (int l = 0; l < 3; ++l) {
+            m.enc[l].b2_16 = m.dev_vec16 + voff.at("e" + std::to_string(l) + ".b2");
+            m.enc[l].b12_16 = m.dev_vec16 + voff.at("e" + std::to_string(l) + ".b12");
+            m.dec[l].b2_16 = m.dev_vec16 + voff.at("d" + std::to_string(l) + ".b2");
+        }
+    }
     CB2_CUDA(cudaMalloc(&m.dev_f16, bp.buf.size() * sizeof(__half)));
     CB2_CUDA(cudaMemcpy(m.dev_f16, bp.buf.data(), bp.buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
     m.n_f16_blocks = (int)(bp.buf.size() / (128 * 128));
@@ -278,6 +299,7 @@ void cb2_denoiser_destroy(cb2_denoiser* d) {
     if (!d) return;
     cudaFree(d->m.dev_f32);
     cudaFree(d->m.dev_f16);
+    cudaFree(d->m.dev_vec16);
     delete d;
 }
 
@@ -396,8 +418,8 @@ int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, 
     e |= dev_alloc(p.allocs, &p.hVenc, N * 128);
     e |= dev_alloc(p.allocs, &p.P, 2 * N * 256);
     if (precision == PREC_F16) {
-        e |= dev_alloc(p.allocs, &p.Pc16[0], N * 128);
-        e |= dev_alloc(p.allocs, &p.Pc16[1], N * 128);
+        e |= dev_alloc(p.allocs, &p.P16[0], N * 256);
+        e |= dev_alloc(p.allocs, &p.P16[1], N * 256);
     }
     e |= dev_alloc(p.allocs, &p.S, N * 128);
     e |= dev_alloc(p.allocs, &p.out6, N * 6);
@@ -405,6 +427,7 @@ int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, 
     e |= dev_alloc(p.allocs, &h->xb, N * 3);
     p.mod_capacity = NB > 1024 ? NB : 1024;
     e |= dev_alloc(p.allocs, &p.mod, (size_t)p.mod_capacity * CB2_MOD_TOTAL);
+    if (precision == PREC_F16) e |= dev_alloc(p.allocs, &p.mod16, (size_t)p.mod_capacity * 768);
     e |= dev_alloc(p.allocs, &p.silu_c, (size_t)p.mod_capacity * 128);
     e |= dev_alloc(p.allocs, &p.tvals, p.mod_capacity);
     e |= dev_alloc(p.allocs, &p.coef, (size_t)p.mod_capacity * 8);
@@ -492,7 +515,7 @@ int cb2_plan_forward_partial(cb2_plan* h, const float* x, const float* t, int st
     if (!h->frames_ready) { set_error("forward_partial: cb2_plan_set_frames has not been called"); return 1; }
     Plan& p = h->p;
     cudaStream_t s = (cudaStream_t)stream;
-    if (int e = launch_timestep_mod(*p.model, t, p.NB, p.silu_c, p.mod, s)) return e;
+    if (int e = launch_timestep_mod(*p.model, t, p.NB, p.silu_c, p.mod, p.mod16, s)) return e;
     p.coef_steps = 0;
     return run_forward(p, x, p.mod, CB2_MOD_TOTAL, nullptr, nullptr, nullptr, s, stop_after);
 }
@@ -503,7 +526,7 @@ int cb2_plan_forward(cb2_plan* h, const float* x, const float* t, float* out, vo
     Plan& p = h->p;
     cudaStream_t s = (cudaStream_t)stream;
     if (p.NB > p.mod_capacity) { set_error("forward: NB exceeds table capacity"); return 1; }
-    if (int e = launch_timestep_mod(*p.model, t, p.NB, p.silu_c, p.mod, s)) return e;
+    if (int e = launch_timestep_mod(*p.model, t, p.NB, p.silu_c, p.mod, p.mod16, s)) return e;
     p.launches += 2;
     p.coef_steps = 0;   // the table no longer holds a sampling schedule
     if (int e = run_forward(p, x, p.mod, CB2_MOD_TOTAL, nullptr, nullptr, nullptr, s)) return e;
@@ -518,7 +541,7 @@ int cb2_plan_set_schedule(cb2_plan* h, const float* t_of_step, const float* coef
     if (T > p.mod_capacity) { set_error("set_schedule: T=%d exceeds capacity %d", T, p.mod_capacity); return 1; }
     CB2_CUDA(cudaMemcpyAsync(p.tvals, t_of_step, T * sizeof(float), cudaMemcpyHostToDevice, s));
     CB2_CUDA(cudaMemcpyAsync(p.coef, coef, (size_t)T * 8 * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (int e = launch_timestep_mod(*p.model, p.tvals, T, p.silu_c, p.mod, s)) return e;
+    if (int e = launch_timestep_mod(*p.model, p.tvals, T, p.silu_c, p.mod, p.mod16, s)) return e;
     CB2_CUDA(cudaStreamSynchronize(s));     // host staging buffers may be freed by the caller on return
     p.launches += 2;
     p.coef_steps = T;
@@ -653,6 +676,10 @@ int cb2_plan_buffer(cb2_plan* h, const char* name, void* dst, long long dst_byte
     else if (n == "hV") { *ptr = p.hV; *bytes = N * 128 * 4; }
     else if (n == "S") { *ptr = p.S; *bytes = N * 128 * 4; }
     else if (n == "out6") { *ptr = p.out6; *bytes = N * 6 * 4; }
+    else if (n == "tc_trace") {
+        if (!p.tc_trace) { unsigned long long* t = nullptr; if (dev_alloc(p.allocs, &t, 1024)) return 1; cudaMemsetAsync(t, 0, 8192, (cudaStream_t)stream); p.tc_trace = t; }
+        *ptr = p.tc_trace; *bytes = 8192;
+    }
     else if (n == "mod") { *ptr = p.mod; *bytes = (size_t)p.mod_capacity * CB2_MOD_TOTAL * 4; }
     else { set_error("plan_buffer: unknown buffer '%s'", name); return 1; }
     if (!src || dst_bytes > size) { set_error("plan_buffer: '%s' holds %lld bytes, %lld requested", name, size, dst_bytes); return 1; }

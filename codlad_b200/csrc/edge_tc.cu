@@ -5,21 +5,23 @@
 //
 //   * edge state h_E, activations and weights are fp16 (kind::f16 MMA, fp32 accumulation in TMEM).  fp16 rather
 //     than bf16: same tensor rate, 8x finer mantissa, and every operand here is LayerNorm/GELU-bounded.
-//   * one CTA per SM (persistent), NWG independent 128-thread "tile pipelines" per CTA that share the layer
-//     weights resident in shared memory (SWIZZLE_128B, K-major, loaded once by TMA).  A tile = NPT whole nodes
-//     (NPT*K <= 128 neighbour rows) of one ensemble member, so the neighbour reduction is tile-local.
+//   * one persistent CTA per SM = two independent 256-thread pipelines that share the layer weights resident in
+//     shared memory (SWIZZLE_128B, K-major, loaded once by TMA).  Each pipeline keeps TWO tiles in flight (two
+//     32 KB operand buffers, two 128-column TMEM accumulators) and interleaves their stages
+//     E1(0) E3(1) E2(0) E1(1) E3(0) E2(1) ..., so a tile's MMA / TMA latency is covered by the other tile's epilogue.
+//     A tile = NPT whole nodes (NPT*K <= 128 neighbour rows) of one ensemble member: the neighbour sum is tile-local.
+//   * thread (row r, column half h): the two warpgroups of a pipeline split the 128 accumulator columns of every row
+//     (both can address TMEM lane r), which halves the per-tile epilogue latency.
 //   * per tile: TMA loads the h_E rows (contiguous in HBM) into a swizzled K-major A tile -> MMA 1 (W?b h_E) ->
-//     epilogue 1 reads the accumulator from TMEM (thread = row), adds the per-node halves of the first layer
-//     (Pa[i] broadcast from smem, Pc[j] gathered from L2 as fp16 with 256-bit loads), GELU, writes the fp16
-//     activation back into the same smem tile -> MMA 2 -> epilogue 2 (+b, GELU) ->
+//     E1: accumulator from TMEM, + own half Pa[i] (L1 broadcast) + gathered half Pc[j] (fp16, 256-bit loads from L2),
+//     GELU, fp16 activation back into the same smem tile -> MMA 2 -> E2 (+b, GELU) ->
 //        ENC_NODE / DEC : the masked neighbour sum is one more (tiny) MMA: S^T[c, q] = sum_r G[r, c] * Ind[q, r]
-//                         with the activation tile reused as an MN-major A operand and a 16-row indicator B;
-//        ENC_EDGE       : MMA 3 (W13) -> epilogue 3: +residual, LayerNorm, adaLN modulate/gate -> fp16 tile ->
-//                         TMA store.
-//     While one pipeline is in an epilogue the tensor core runs another pipeline's MMAs.
-//   * GELU uses tanh.approx (one MUFU per element) on a refitted 2-term inner polynomial: |err| < 2.8e-4 abs
-//     against erf-GELU before the MUFU's own 2^-11 relative error -- the same order as the fp16 rounding of the
-//     activation it feeds.  (The fp32 tier uses erff.)
+//                         with the activation tile reused as an MN-major A operand and a 16-row indicator B; E3 stores S;
+//        ENC_EDGE       : MMA 3 (W13) -> E3: +residual, LayerNorm (row statistics exchanged between the two column
+//                         halves through 1 KB of smem), adaLN modulate/gate -> fp16 tile -> TMA store.
+//   * epilogue arithmetic is packed fp16 (HFMA2); GELU uses tanh.approx (one MUFU per element) on a refitted 2-term
+//     inner polynomial: |err| < 2.8e-4 abs against erf-GELU before the MUFU's own 2^-11 relative error -- the same
+//     order as the fp16 rounding of the activation it feeds.  (The fp32 tier uses erff.)
 #include "model.h"
 #include "tc_common.cuh"
 
@@ -39,18 +41,19 @@ struct TcMaps {
 };
 
 struct TcParams {
-    int mode, L, K, NPT, tiles_per_member, n_tiles;
+    int L, K, NPT, tiles_per_member, n_tiles;
     int in_is_frame;                 // layer 0 of the encoder reads h_E0 (indexed by frame)
     int w_row[3];                    // first row of each weight block in the packed weight tensor
     int n_w;                         // 2 (ENC_NODE / DEC) or 3 (ENC_EDGE)
-    const float* P;                  // [N, 256]: [:, :128] = Wa h_V_i + b1 (own half)
-    const __half* Pc;                // [N, 128]: gathered half Wc h_V_j (+ decoder table), fp16
-    const float *b2, *b3;            // second / third layer biases (fp32)
-    const float* mod;                // ENC_EDGE: adaLN block of this layer; member row at mod + b * mod_stride
-    int mod_stride;
+    const __half* P16;               // [N, 256] fp16: [own half Wa h_V_i + b1 | gathered half Wc h_V_j (+ decoder table)]
+    const __half* b2h;               // [128] second-layer bias, fp16
+    const float* b3;                 // [128] third-layer bias (ENC_EDGE), fp32
+    const __half* mod16;             // ENC_EDGE: [rows, 3, 256] gate (1 + scale) | gate * shift; member row at b * mod16_stride
+    int mod16_stride;
     const __half* res;               // ENC_EDGE: residual source (= the tile's input rows)
     const int *lengths, *frame_of, *nbr_idx;
     float* S;                        // [N, 128] neighbour sums (ENC_NODE / DEC)
+    unsigned long long* trace;       // debug: stage timestamps of CTA 0 (nullptr = off)
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -72,337 +75,406 @@ __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
     const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
     return __hfma2(h, as_h2(t), h);
 }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the 256 epilogue threads only
 
-struct TileMeta {
-    int b, i0, nv;
-    int in_row0, out_row0;
-    size_t node0;
-    bool row_valid, row_on;
-    int q_of_r;
-    const __half* pc_row;
-    float pa[MAX_NPT];
-    float modA, modB;        // ENC_EDGE: gate (1 + scale) and gate * shift of this thread's column
+struct TileMeta {            // per-thread view of a tile (kept small: four of them live in registers)
+    int tile;                // global tile index (>= n_tiles: this slot has run out of work)
+    int nv;                  // valid nodes in the tile
+    int in_row0;             // first edge row of the tile in the input tensor (ENC_EDGE residual)
+    int node0;               // first node (member indexing)
+    uint32_t keep;           // 0xffffffff if this row takes part in the neighbour sum
+    int pa_node;             // this thread's node          -> own half      P16[pa_node][c0 ...]
+    int pc_node;             // this thread's neighbour     -> gathered half P16[pc_node][128 + c0 ...]
+    int member;              // ENC_EDGE: row of mod16
 };
 
-template <int NWG, int MODE>
-__global__ void __launch_bounds__(NWG * 128, 1) edge_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms repeat every 1 KiB
-    // layout: [weights n_w x 32 KB][tiles NWG x 32 KB][indicator 4 KB][CTA vectors][per-WG vectors][barriers]
+constexpr int EPI_THREADS = 256;                // thread (row r, column half h): two warpgroups split the accumulator columns
+constexpr int CTA_THREADS = EPI_THREADS + 64;   // + two control warps (one lane each): MMA issue, TMA issue
+constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 KB operand buffer + 128 TMEM columns each)
+
+template <int MODE>
+__global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int N_W = MODE == EDGE_ENC_EDGE ? 3 : 2;
+    // layout: [weights N_W x 32 KB][4 tile slots x 32 KB][indicator 4 KB | LN exchange 1 KB][barriers]
     unsigned char* sW = smem;
-    unsigned char* sT = sW + p.n_w * TILE_BYTES;
-    unsigned char* sInd = sT + NWG * TILE_BYTES;
-    __half* sB2h = reinterpret_cast<__half*>(sInd + IND_BYTES);          // [128] second-layer bias, fp16
-    float* sB3 = reinterpret_cast<float*>(sB2h + 128);                   // [128] third-layer bias, fp32
-    __half* sWgVec = reinterpret_cast<__half*>(sB3 + 128);               // per WG: Pa[MAX_NPT][128], modA[128], modB[128]
-    constexpr int VEC_PER_WG = (MAX_NPT + 2) * 128;
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sWgVec + NWG * VEC_PER_WG);   // [0] weights, [1 + 2 wg] load, [2 + 2 wg] mma
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1 + 2 * NWG);
+    unsigned char* sT = sW + N_W * TILE_BYTES;
+    unsigned char* sAux = sT + 4 * TILE_BYTES;
+    unsigned char* sInd = sAux;                                                   // ENC_NODE / DEC
+    float2* sXchg = reinterpret_cast<float2*>(sAux);                              // ENC_EDGE: [128 rows]
+    // barriers: [0] weights; per tile slot g: [1+3g] load (TMA tx), [2+3g] acc (MMA commit), [3+3g] epi (256 arrivals)
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sAux + (MODE == EDGE_ENC_EDGE ? 1024 : IND_BYTES));
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 17);
 
-    const int tid = threadIdx.x, wg = tid >> 7, wt = tid & 127, warp_in_wg = wt >> 5;
+    const int tid = threadIdx.x;
     const int K = p.K, NPT = p.NPT;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();                                   // SWIZZLE_128B atoms repeat every 1 KiB
 
-    // ---- one-time setup: barriers, TMEM, weights, indicator operand ----
+    // ---- one-time setup: barriers, TMEM, indicator operand ----
     if (tid == 0) {
         mbar_init(smem_u32(&sBar[0]), 1);
-        for (int g = 0; g < NWG; ++g) { mbar_init(smem_u32(&sBar[1 + 2 * g]), 1); mbar_init(smem_u32(&sBar[2 + 2 * g]), 1); }
+        for (int g = 0; g < 4; ++g) {
+            mbar_init(smem_u32(&sBar[1 + 3 * g]), 1);
+            mbar_init(smem_u32(&sBar[2 + 3 * g]), 1);
+            mbar_init(smem_u32(&sBar[3 + 3 * g]), 256);
+            mbar_init(smem_u32(&sBar[13 + g]), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) {
+    if (tid >= EPI_THREADS && tid < EPI_THREADS + 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(sTmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // indicator B operand of the reduction MMA: Ind[q][r] = 1 if row r belongs to node q (K-major SW128, 16 rows x 128 k)
-    for (int t = tid; t < 16 * 16; t += NWG * 128) {
-        const int q = t >> 4, c16 = t & 15;
-        uint32_t w[4];
+    if (MODE != EDGE_ENC_EDGE) {
+        // indicator B operand of the reduction MMA: Ind[q][r] = 1 if row r belongs to node q (K-major SW128, 16 rows x 128 k)
+        for (int t = tid; t < 16 * 16; t += CTA_THREADS) {
+            const int q = t >> 4, c16 = t & 15;
+            uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int r0 = c16 * 8 + e * 2;
-            const __half lo = __float2half((q < NPT && r0 / K == q) ? 1.f : 0.f);
-            const __half hi = __float2half((q < NPT && (r0 + 1) / K == q) ? 1.f : 0.f);
-            w[e] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+            for (int e = 0; e < 4; ++e) {
+                const int r0 = c16 * 8 + e * 2;
+                const __half lo = __float2half((q < NPT && r0 / K == q) ? 1.f : 0.f);
+                const __half hi = __float2half((q < NPT && (r0 + 1) / K == q) ? 1.f : 0.f);
+                w[e] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+            }
+            const uint32_t off = (uint32_t)((c16 >> 3) * (16 * 128) + q * 128 + (((c16 & 7) ^ (q & 7)) << 4));
+            *reinterpret_cast<uint4*>(sInd + off) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        const uint32_t off = (uint32_t)((c16 >> 3) * (16 * 128) + q * 128 + (((c16 & 7) ^ (q & 7)) << 4));
-        *reinterpret_cast<uint4*>(sInd + off) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    if (tid < 128) {
-        sB2h[tid] = __float2half_rn(p.b2[tid]);
-        sB3[tid] = MODE == EDGE_ENC_EDGE ? p.b3[tid] : 0.f;
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
-    if (tid == 0) {
-        mbar_expect_tx(smem_u32(&sBar[0]), (uint32_t)(p.n_w * TILE_BYTES));
-        for (int m = 0; m < p.n_w; ++m)
-            for (int h = 0; h < 2; ++h)
-                tma_load_2d(smem_u32(sW + m * TILE_BYTES + h * HALF_BYTES), &maps.weights, h * 64, p.w_row[m], smem_u32(&sBar[0]));
-    }
-
-    unsigned char* T = sT + wg * TILE_BYTES;
-    const uint32_t T_u32 = smem_u32(T);
-    __half* sPa = sWgVec + wg * VEC_PER_WG;
-    __half* sModA = sPa + MAX_NPT * 128;
-    __half* sModB = sModA + 128;
-    const uint32_t bar_load = smem_u32(&sBar[1 + 2 * wg]), bar_mma = smem_u32(&sBar[2 + 2 * wg]);
-    const uint32_t tmem_acc = tmem_base + (uint32_t)(wg * 128);                       // this pipeline's 128 accumulator columns
-    const uint32_t tmem_row = tmem_acc + ((uint32_t)(warp_in_wg * 32) << 16);         // + this warp's lane quarter
-    const CUtensorMap* in_map = p.in_is_frame ? &maps.in_frame : &maps.state;
+    const int tile_stride = gridDim.x * 4;
     constexpr uint32_t IDESC_MAIN = umma_idesc(128, 128, 0, 0);
     constexpr uint32_t IDESC_RED = umma_idesc(128, 16, 1, 0);
-    uint32_t ph_load = 0, ph_mma = 0;
-    bool weights_ready = false;
-    const int r = wt;                          // this thread's tile row == TMEM lane
-    const int tile_stride = gridDim.x * NWG;
 
-    // per-tile metadata: every global load it needs is issued one tile ahead
-    auto load_meta = [&](int tile) {
-        TileMeta m;
-        m.b = tile / p.tiles_per_member;
-        m.i0 = (tile - m.b * p.tiles_per_member) * NPT;
-        m.nv = min(NPT, p.L - m.i0);
-        const int f = p.frame_of[m.b];
-        const int len = p.lengths[f];
-        m.node0 = (size_t)m.b * p.L + m.i0;
-        m.in_row0 = (int)(((size_t)(p.in_is_frame ? f : m.b) * p.L + m.i0) * K);
-        m.out_row0 = (int)(m.node0 * K);
-        m.q_of_r = r / K;
-        m.row_valid = m.q_of_r < m.nv;
-        int j = 0;
-        m.row_on = false;
-        if (m.row_valid) {
-            const int i = m.i0 + m.q_of_r;
-            j = p.nbr_idx[((size_t)f * p.L + i) * K + (r - m.q_of_r * K)];
-            m.row_on = (MODE == EDGE_DEC) ? true : (i < len && j < len);
-        }
-        m.pc_row = p.Pc + ((size_t)m.b * p.L + j) * 128;
-#pragma unroll
-        for (int q = 0; q < MAX_NPT; ++q) m.pa[q] = q < m.nv ? p.P[(m.node0 + q) * 256 + wt] : 0.f;
-        m.modA = 0.f; m.modB = 0.f;
-        if (MODE == EDGE_ENC_EDGE) {
-            const float* md = p.mod + (size_t)m.b * p.mod_stride;
-            const float gate = md[1024 + wt];
-            m.modA = gate * (1.0f + md[896 + wt]);
-            m.modB = gate * md[768 + wt];
-        }
-        return m;
-    };
-    auto issue_load = [&](const TileMeta& m) {          // one thread: TMA of the tile's h_E rows, one box per node and half
-        mbar_expect_tx(bar_load, (uint32_t)(m.nv * K * 256));
-        for (int q = 0; q < m.nv; ++q)
-            for (int h = 0; h < 2; ++h)
-                tma_load_2d(T_u32 + h * HALF_BYTES + q * K * 128, in_map, h * 64, m.in_row0 + q * K, bar_load);
-    };
-    auto issue_mma = [&](int w_slot) {                  // one thread: 128x128x128 GEMM, A = activation tile, B = weight slot
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-            umma_f16(tmem_acc, umma_desc(T_u32 + koff, 16, 1024), umma_desc(smem_u32(sW + w_slot * TILE_BYTES) + koff, 16, 1024), IDESC_MAIN, k > 0);
-        }
-        umma_commit(bar_mma);
-    };
-
-    int tile = blockIdx.x * NWG + wg;
-    TileMeta nxt{};
-    if (tile < p.n_tiles) {
-        nxt = load_meta(tile);
-        if (wt == 0) issue_load(nxt);
-    }
-    while (tile < p.n_tiles) {
-        const TileMeta cur = nxt;
-        const int next_tile = tile + tile_stride;
-        // ---- stage this tile's per-node / per-member vectors ----
-#pragma unroll
-        for (int q = 0; q < MAX_NPT; ++q) sPa[q * 128 + wt] = __float2half_rn(cur.pa[q]);
-        if (MODE == EDGE_ENC_EDGE) { sModA[wt] = __float2half_rn(cur.modA); sModB[wt] = __float2half_rn(cur.modB); }
-        wg_sync(wg);
-        if (!weights_ready) { mbar_wait(smem_u32(&sBar[0]), 0); weights_ready = true; }
-        uint32_t pc0[16], pc1[16];                       // gathered Pc[j] chunks (32 halves each), double buffered
-        {
-            uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pc0[0]);
-            uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pc0[8]);
-            ldg256(cur.pc_row, lo); ldg256(cur.pc_row + 16, hi);
-        }
-        mbar_wait(bar_load, ph_load); ph_load ^= 1;
-
-        // ---- MMA 1: acc = h_E . W?b^T ; then prefetch the next tile's metadata while it runs ----
-        if (wt == 0) issue_mma(0);
-        if (next_tile < p.n_tiles) nxt = load_meta(next_tile);
-        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
-        tc_fence_after();
-
-        // ---- epilogue 1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile (packed-half arithmetic) ----
-        {
-            const __half* pa_row = sPa + (cur.row_valid ? cur.q_of_r : 0) * 128;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t (&pcc)[16] = (c & 1) ? pc1 : pc0;
-                uint32_t (&pcn)[16] = (c & 1) ? pc0 : pc1;
-                if (c < 3) {
-                    uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pcn[0]);
-                    uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pcn[8]);
-                    ldg256(cur.pc_row + (c + 1) * 32, lo); ldg256(cur.pc_row + (c + 1) * 32 + 16, hi);
-                }
-                float acc[32];
-                tmem_ld32(tmem_row + c * 32, acc);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint4 pav = *reinterpret_cast<const uint4*>(pa_row + c * 32 + u * 8);
-                    const uint32_t pa4[4] = {pav.x, pav.y, pav.z, pav.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(pa4[e])), as_h2(pcc[u * 4 + e]));
-                        o[e] = as_u32(gelu_h2(x));
+    if (tid >= EPI_THREADS) {
+        // =========================================================================== control warps (one lane each)
+        // warp 8 issues every MMA, warp 9 every TMA, in the order the epilogue warps consume them: the epilogue
+        // threads never execute issue code and a tile's MMA / TMA latency is covered by the other tiles' epilogues.
+        // (MMA and TMA issue are split because a thread's tcgen05.mma stalls behind its own in-flight bulk copies.)
+        auto T_u32 = [&](int g) { return smem_u32(sT + g * TILE_BYTES); };
+        auto bar_load = [&](int g) { return smem_u32(&sBar[1 + 3 * g]); };
+        auto bar_acc = [&](int g) { return smem_u32(&sBar[2 + 3 * g]); };
+        auto bar_epi = [&](int g) { return smem_u32(&sBar[3 + 3 * g]); };
+        auto bar_go = [&](int g) { return smem_u32(&sBar[13 + g]); };          // slot g's operand tile may be recycled
+        if (tid == EPI_THREADS + 32) {
+            // ------------------------------------------------------------------ TMA thread
+            const CUtensorMap* in_map = p.in_is_frame ? &maps.in_frame : &maps.state;
+            mbar_expect_tx(smem_u32(&sBar[0]), (uint32_t)(N_W * TILE_BYTES));
+            for (int m = 0; m < N_W; ++m)
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d(smem_u32(sW + m * TILE_BYTES + h * HALF_BYTES), &maps.weights, h * 64, p.w_row[m], smem_u32(&sBar[0]));
+            int nv[4], out_row0[4];
+            auto issue_load = [&](int g, int t) {                     // TMA of the tile's h_E rows, one box per node and half
+                const int b = t / p.tiles_per_member;
+                const int i0 = (t - b * p.tiles_per_member) * NPT;
+                nv[g] = min(NPT, p.L - i0);
+                const int in_row0 = ((p.in_is_frame ? __ldg(p.frame_of + b) : b) * p.L + i0) * K;
+                out_row0[g] = (b * p.L + i0) * K;
+                mbar_expect_tx(bar_load(g), (uint32_t)(nv[g] * K * 256));
+                for (int q = 0; q < nv[g]; ++q)
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d(T_u32(g) + h * HALF_BYTES + q * K * 128, in_map, h * 64, in_row0 + q * K, bar_load(g));
+            };
+            for (int g = 0; g < 4; ++g)
+                if (blockIdx.x * 4 + g < p.n_tiles) issue_load(g, blockIdx.x * 4 + g);
+            uint32_t ph_go = 0;
+            for (int t0 = blockIdx.x * 4; t0 < p.n_tiles; t0 += tile_stride) {
+                for (int g = 0; g < 4; ++g) {
+                    const int t = t0 + g;
+                    if (t >= p.n_tiles) break;
+                    mbar_wait(bar_go(g), ph_go);                      // reduction MMA complete (ENC_NODE / DEC) or E3 done (ENC_EDGE)
+                    if (MODE == EDGE_ENC_EDGE) {
+                        for (int q = 0; q < nv[g]; ++q)
+                            for (int h = 0; h < 2; ++h)
+                                tma_store_2d(&maps.state, h * 64, out_row0[g] + q * K, T_u32(g) + h * HALF_BYTES + q * K * 128);
+                        tma_store_commit();
                     }
-                    *reinterpret_cast<uint4*>(T + tile_off(r, c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-        }
-        fence_async_smem();
-        tc_fence_before();
-        wg_sync(wg);
-
-        // ---- MMA 2 ----
-        if (wt == 0) issue_mma(1);
-        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
-        tc_fence_after();
-
-        // ---- epilogue 2: GELU(acc + b2) (masked rows -> 0 for the reduction) -> fp16 tile ----
-        {
-            const uint32_t keep = (MODE == EDGE_ENC_EDGE || cur.row_on) ? 0xffffffffu : 0u;     // bit mask: no branch per pair
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float acc[32];
-                tmem_ld32(tmem_row + c * 32, acc);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint4 bv = *reinterpret_cast<const uint4*>(sB2h + c * 32 + u * 8);
-                    const uint32_t b4[4] = {bv.x, bv.y, bv.z, bv.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __half2 x = __hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(b4[e]));
-                        o[e] = as_u32(gelu_h2(x)) & keep;
+                    if (t + tile_stride < p.n_tiles) {
+                        if (MODE == EDGE_ENC_EDGE) tma_store_wait_read();        // the store has finished reading the tile
+                        issue_load(g, t + tile_stride);
                     }
-                    *reinterpret_cast<uint4*>(T + tile_off(r, c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+                ph_go ^= 1;
             }
-        }
-        fence_async_smem();
-        tc_fence_before();
-        wg_sync(wg);
-
-        if (MODE != EDGE_ENC_EDGE) {
-            // ---- neighbour sum as an MMA: D[c, q] = sum_r G[r, c] Ind[q, r]  (A = G^T, MN-major view of the tile) ----
-            if (wt == 0) {
+            if (MODE == EDGE_ENC_EDGE) tma_store_wait_all();
+        } else if (tid == EPI_THREADS) {
+            // ------------------------------------------------------------------ MMA thread
+            uint32_t ph_load = 0, ph_epi = 0;
+            auto issue_mma = [&](int g, int w_slot) {                 // 128x128x128 GEMM, A = tile g, B = weight slot
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const uint64_t a = umma_desc(T_u32 + (uint32_t)(k * 16 * 128), HALF_BYTES, 1024);      // 16 rows (K) per step
+                    const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
+                    umma_f16(tmem_base + (uint32_t)(g * 128), umma_desc(T_u32(g) + koff, 16, 1024),
+                             umma_desc(smem_u32(sW + w_slot * TILE_BYTES) + koff, 16, 1024), IDESC_MAIN, k > 0);
+                }
+                umma_commit(bar_acc(g));
+            };
+            auto issue_reduce = [&](int g) {                          // D[c, q] = sum_r G[r, c] Ind[q, r]
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t a = umma_desc(T_u32(g) + (uint32_t)(k * 16 * 128), HALF_BYTES, 1024);   // A = G^T: MN-major view, 16 rows (K) per step
                     const uint64_t bd = umma_desc(smem_u32(sInd) + (uint32_t)((k >> 2) * (16 * 128) + (k & 3) * 32), 16, 1024);
-                    umma_f16(tmem_acc, a, bd, IDESC_RED, k > 0);
+                    umma_f16(tmem_base + (uint32_t)(g * 128), a, bd, IDESC_RED, k > 0);
                 }
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
-            tc_fence_after();
-            if (wt == 0 && next_tile < p.n_tiles) issue_load(nxt);       // T is free: start the next tile's TMA now
-            float s4[4];
-            tmem_ld4(tmem_row, s4);             // lane = output column, 4 columns = nodes of the tile
-#pragma unroll
-            for (int q = 0; q < MAX_NPT; ++q)
-                if (q < cur.nv) p.S[(cur.node0 + q) * 128 + wt] = s4[q];
-            tc_fence_before();
-            wg_sync(wg);                        // TMEM and the per-tile vectors are reused by the next tile
-        } else {
-            // ---- MMA 3 (W13), then residual + LayerNorm + adaLN -> fp16 tile -> TMA store ----
-            const __half* res_row = p.res + ((size_t)cur.in_row0 + (cur.row_valid ? r : 0)) * 128;
-            uint32_t rs0[16], rs1[16];
-            {
-                uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rs0[0]);
-                uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rs0[8]);
-                ldg256_coherent(res_row, lo); ldg256_coherent(res_row + 16, hi);
-            }
-            if (wt == 0) issue_mma(2);
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
-            tc_fence_after();
-            // pass A (fp32): v = residual + acc + b13, row statistics; v is parked as fp16 in this thread's tile row
-            float sum = 0.f, sq = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t (&rc)[16] = (c & 1) ? rs1 : rs0;
-                uint32_t (&rn)[16] = (c & 1) ? rs0 : rs1;
-                if (c < 3) {
-                    uint32_t (&lo)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rn[0]);
-                    uint32_t (&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rn[8]);
-                    ldg256_coherent(res_row + (c + 1) * 32, lo); ldg256_coherent(res_row + (c + 1) * 32 + 16, hi);
+                umma_commit(bar_acc(g));
+                umma_commit(bar_go(g));                                // ... and the operand tile is free once these MMAs complete
+            };
+            mbar_wait(smem_u32(&sBar[0]), 0);                         // weights resident
+            uint32_t round = 0;
+            for (int t0 = blockIdx.x * 4; t0 < p.n_tiles; t0 += tile_stride, ++round) {
+                const int n = min(4, p.n_tiles - t0);                  // live slots of this round
+                const int n_next = max(0, min(4, p.n_tiles - (t0 + tile_stride)));
+                if (round == 0)
+                    for (int g = 0; g < n; ++g) { mbar_wait(bar_load(g), 0); issue_mma(g, 0); }                // TMA landed -> MMA 1
+                for (int g = 0; g < n; ++g) { mbar_wait(bar_epi(g), ph_epi); issue_mma(g, 1); }                // E1 done -> MMA 2
+                ph_epi ^= 1;
+                for (int g = 0; g < n; ++g) {                                                                  // E2 done -> reduction MMA / MMA 3
+                    mbar_wait(bar_epi(g), ph_epi);
+                    if (MODE == EDGE_ENC_EDGE) issue_mma(g, 2); else issue_reduce(g);
                 }
+                ph_epi ^= 1;
+                // E3 done: the accumulator is drained -> MMA 1 of the slot's next tile as soon as its TMA has landed.
+                // ENC_EDGE recycles the operand tile only now (store, then reload), so its MMA 1 trails by one slot.
+                const uint32_t next_parity = (round + 1) & 1;
+                for (int g = 0; g < n; ++g) {
+                    mbar_wait(bar_epi(g), ph_epi);
+                    if (MODE == EDGE_ENC_EDGE) mbar_arrive(bar_go(g));                                         // tile complete in smem: store + recycle
+                    const int h = MODE == EDGE_ENC_EDGE ? g - 1 : g;
+                    if (h >= 0 && h < n_next) { mbar_wait(bar_load(h), next_parity); issue_mma(h, 0); }
+                }
+                if (MODE == EDGE_ENC_EDGE && n - 1 < n_next) { mbar_wait(bar_load(n - 1), next_parity); issue_mma(n - 1, 0); }
+                ph_epi ^= 1;
+            }
+            (void)ph_load;
+        }
+    } else {
+        // =========================================================================== epilogue threads
+        const int half = tid >> 7, r = tid & 127, quarter = (tid >> 5) & 3;
+        const int c0 = half * 64;                                      // this thread's 64 accumulator columns
+        auto T_of = [&](int s) { return sT + s * TILE_BYTES; };
+        auto bar_acc = [&](int s) { return smem_u32(&sBar[2 + 3 * s]); };
+        auto bar_epi = [&](int s) { return smem_u32(&sBar[3 + 3 * s]); };
+        auto tmem_row = [&](int s) { return tmem_base + (uint32_t)(s * 128) + ((uint32_t)(quarter * 32) << 16); };
+        auto done = [&](int s) { fence_async_smem(); tc_fence_before(); mbar_arrive(bar_epi(s)); };     // (mark(6) follows in the callers)
+
+        // per-tile metadata (its global loads are issued a full tile ahead of their use)
+        auto load_meta = [&](int tile) {
+            TileMeta m{};
+            m.tile = tile;
+            if (tile >= p.n_tiles) return m;
+            const int b = tile / p.tiles_per_member;
+            const int i0 = (tile - b * p.tiles_per_member) * NPT;
+            m.nv = min(NPT, p.L - i0);
+            const int f = __ldg(p.frame_of + b);                        // tiny arrays: L1 hits
+            const int len = __ldg(p.lengths + f);
+            m.node0 = b * p.L + i0;
+            m.in_row0 = ((p.in_is_frame ? f : b) * p.L + i0) * K;
+            const int q = r / K;
+            int j = 0, qq = 0;
+            m.keep = 0u;
+            if (q < m.nv) {
+                const int i = i0 + q;
+                qq = q;
+                j = __ldg(p.nbr_idx + ((size_t)f * p.L + i) * K + (r - q * K));
+                m.keep = (MODE == EDGE_DEC || (i < len && j < len)) ? 0xffffffffu : 0u;
+            }
+            m.pa_node = m.node0 + qq;
+            m.pc_node = b * p.L + j;
+            m.member = b;
+            return m;
+        };
+        unsigned long long* trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
+        int n_trace = 0;
+        auto mark = [&](int ev, int s) {
+            if (trace != nullptr && n_trace < 1000) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                trace[1 + n_trace] = (t << 8) | (unsigned long long)((ev << 2) | s);
+                trace[0] = (unsigned long long)(++n_trace);
+            }
+        };
+        TileMeta meta[NSLOT];
+        uint32_t ph_acc[NSLOT] = {0, 0, 0, 0};
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) meta[s] = load_meta(blockIdx.x * NSLOT + s);
+
+        // ---- E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile ----
+        auto epi1 = [&](int s) {
+            const TileMeta& m = meta[s];
+            unsigned char* T = T_of(s);
+            uint32_t pc[32], pa[32];                                     // this thread's 64 gathered / own halves: loads in flight
+#pragma unroll                                                          // while the MMA completes
+            for (int q = 0; q < 4; ++q) ldg256(p.P16 + (size_t)m.pc_node * 256 + 128 + c0 + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[q * 8]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ldg256(p.P16 + (size_t)m.pa_node * 256 + c0 + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[q * 8]));
+            mark(0, s);
+            mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
+            tc_fence_after();
+            mark(1, s);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 float acc[32];
-                tmem_ld32(tmem_row + c * 32, acc);
+                tmem_ld32(tmem_row(s) + c0 + c * 32, acc);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int col = u * 8 + e * 2;
-                        const float2 rr = h2_to_f2(rc[u * 4 + e]);
-                        const float2 bb = *reinterpret_cast<const float2*>(sB3 + c * 32 + col);
-                        const float v0 = rr.x + (acc[col] + bb.x), v1 = rr.y + (acc[col + 1] + bb.y);
-                        sum += v0 + v1;
-                        sq = fmaf(v0, v0, fmaf(v1, v1, sq));
-                        o[e] = pack_sat(v0, v1);
+                        const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(pa[c * 16 + u * 4 + e])),
+                                                  as_h2(pc[c * 16 + u * 4 + e]));
+                        o[e] = as_u32(gelu_h2(x));
                     }
-                    *reinterpret_cast<uint4*>(T + tile_off(r, c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
-            const float mean = sum * (1.0f / 128.0f);
-            const float var = fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f);
-            const __half2 rstd2 = __float2half2_rn(rsqrtf(var + 1e-6f));
-            const __half2 mean2 = __float2half2_rn(mean);
-            // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
+            done(s);
+            mark(6, s);
+        };
+        // ---- E2: GELU(acc + b2) (masked rows -> 0 for the reduction) -> fp16 tile ----
+        auto epi2 = [&](int s) {
+            const TileMeta& m = meta[s];
+            unsigned char* T = T_of(s);
+            const uint32_t keep = MODE == EDGE_ENC_EDGE ? 0xffffffffu : m.keep;
+            uint32_t b2r[32];                                            // second-layer bias of this thread's 64 columns (fp16 pairs)
 #pragma unroll
-            for (int c16 = 0; c16 < 16; ++c16) {
-                uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, c16));
-                const uint4 vv = *slot;
-                const uint4 av = *reinterpret_cast<const uint4*>(sModA + c16 * 8);
-                const uint4 bv = *reinterpret_cast<const uint4*>(sModB + c16 * 8);
-                const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w}, a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
-                uint32_t o[4];
+            for (int q = 0; q < 4; ++q) ldg256(p.b2h + c0 + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&b2r[q * 8]));
+            mark(2, s);
+            mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
+            tc_fence_after();
+            mark(3, s);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
-                *slot = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            wg_sync(wg);
-            if (wt == 0) {
-                for (int q = 0; q < cur.nv; ++q)
-                    for (int h = 0; h < 2; ++h)
-                        tma_store_2d(&maps.state, h * 64, cur.out_row0 + q * K, T_u32 + h * HALF_BYTES + q * K * 128);
-                tma_store_commit();
-                if (next_tile < p.n_tiles) {
-                    tma_store_wait_read();                               // the store has finished reading T
-                    issue_load(nxt);
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t* bb = b2r + c * 16;
+                float acc[32];
+                tmem_ld32(tmem_row(s) + c0 + c * 32, acc);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 x = __hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(bb[u * 4 + e]));
+                        o[e] = as_u32(gelu_h2(x)) & keep;
+                    }
+                    *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
+            done(s);
+            mark(6, s);
+        };
+        // ---- E3: finish the tile, fetch the metadata of the slot's next tile ----
+        auto epi3 = [&](int s) {
+            const TileMeta m = meta[s];
+            unsigned char* T = T_of(s);
+            const int next_tile = m.tile + tile_stride;
+            if (MODE != EDGE_ENC_EDGE) {
+                meta[s] = load_meta(next_tile);
+                mark(4, s);
+                mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
+                tc_fence_after();
+                mark(5, s);
+                if (half == 0) {
+                    float s4[4];
+                    tmem_ld4(tmem_row(s), s4);                // lane = output column, 4 columns = nodes of the tile
+#pragma unroll
+                    for (int q = 0; q < MAX_NPT; ++q)
+                        if (q < m.nv) p.S[((size_t)m.node0 + q) * 128 + r] = s4[q];
+                }
+                done(s);                                      // accumulator drained: the slot's next MMA 1 may start
+            } else {
+                const __half* res_row = p.res + ((size_t)m.in_row0 + (r < m.nv * K ? r : 0)) * 128 + c0;
+                uint32_t rs[32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ldg256_coherent(res_row + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&rs[q * 8]));
+                mark(4, s);
+                mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
+                tc_fence_after();
+                mark(5, s);
+                // pass A (fp32): v = residual + acc + b13, partial row statistics; v is parked as fp16 in the tile
+                float sum = 0.f, sq = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float acc[32];
+                    tmem_ld32(tmem_row(s) + c0 + c * 32, acc);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = u * 8 + e * 2;
+                            const float2 rr = h2_to_f2(rs[c * 16 + u * 4 + e]);
+                            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b3 + c0 + c * 32 + col));
+                            const float v0 = rr.x + (acc[col] + bb.x), v1 = rr.y + (acc[col + 1] + bb.y);
+                            sum += v0 + v1;
+                            sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+                            o[e] = pack_sat(v0, v1);
+                        }
+                        *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                // row statistics: the two column halves of a row live in different warpgroups
+                float2* xr = sXchg + r;
+                if (half == 1) *xr = make_float2(sum, sq);
+                epi_sync();
+                float mean = 0.f, rstd = 0.f;
+                if (half == 0) {
+                    const float2 o = *xr;
+                    sum += o.x; sq += o.y;
+                    mean = sum * (1.0f / 128.0f);
+                    rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
+                    *xr = make_float2(mean, rstd);
+                }
+                meta[s] = load_meta(next_tile);
+                epi_sync();
+                if (half == 1) { const float2 o = *xr; mean = o.x; rstd = o.y; }
+                const __half2 rstd2 = __float2half2_rn(rstd), mean2 = __float2half2_rn(mean);
+                const __half* mod_row = p.mod16 + (size_t)m.member * p.mod16_stride;
+                // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) {
+                    uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16));
+                    const uint4 vv = *slot;
+                    const uint4 av = __ldg(reinterpret_cast<const uint4*>(mod_row + c0 + c16 * 8));
+                    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(mod_row + 128 + c0 + c16 * 8));
+                    const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w}, a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
+                    *slot = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                done(s);                                      // tile complete: the control warp stores it and reloads the slot
+            }
+            mark(6, s);
+        };
+
+        // the slots advance in lock step (a slot that has run out of tiles is skipped): between two stages of a
+        // tile the other three tiles' stages run, which is what hides the MMA / TMA latency
+        while (meta[0].tile < p.n_tiles) {             // tiles are dealt in slot order, so slot 0 is the last to run dry
+            bool on[NSLOT];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) on[s] = meta[s].tile < p.n_tiles;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) if (on[s]) epi1(s);
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) if (on[s]) epi2(s);
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) if (on[s]) epi3(s);
         }
-        tile = next_tile;
     }
-    if (MODE == EDGE_ENC_EDGE && wt == 0) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (tid >= EPI_THREADS && tid < EPI_THREADS + 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-size_t tc_smem_bytes(int nwg, int n_w) {
-    return (size_t)n_w * TILE_BYTES + (size_t)nwg * TILE_BYTES + IND_BYTES + 128 * 2 + 128 * 4 + (size_t)nwg * (MAX_NPT + 2) * 128 * 2 +
-           (1 + 2 * nwg) * 8 + 16 + 1024 /* alignment slack */;
+size_t tc_smem_bytes(int mode) {
+    const int n_w = mode == EDGE_ENC_EDGE ? 3 : 2;
+    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 1024 : IND_BYTES) + 17 * 8 + 16;
 }
 
 }  // namespace
@@ -419,9 +491,9 @@ int edge_tc_prepare(Plan& p) {
     int dev = 0;
     CB2_CUDA(cudaGetDevice(&dev));
     CB2_CUDA(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<4, EDGE_ENC_NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4, 2)));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<4, EDGE_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4, 2)));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<3, EDGE_ENC_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(3, 3)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_NODE)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_DEC)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_EDGE)));
     return 0;
 }
 
@@ -434,40 +506,38 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     const DenoiserModel& m = *p.model;
     const TcMaps& maps = *reinterpret_cast<const TcMaps*>(p.tmaps);
     TcParams tp{};
-    tp.mode = mode; tp.L = p.L; tp.K = p.K;
+    tp.L = p.L; tp.K = p.K;
     tp.NPT = 128 / p.K < MAX_NPT ? 128 / p.K : MAX_NPT;
     if (tp.NPT < 1 || p.K % 8 != 0) tp.NPT = 1;      // node row blocks must start on a swizzle-atom (8-row) boundary
     tp.tiles_per_member = (p.L + tp.NPT - 1) / tp.NPT;
     tp.n_tiles = tp.tiles_per_member * p.NB;
     tp.lengths = p.lengths; tp.frame_of = p.frame_of; tp.nbr_idx = p.nbr_idx; tp.S = p.S;
-    tp.mod_stride = mod_stride_b;
+    tp.trace = p.tc_trace;
     const bool first = (layer == 0 && mode != EDGE_DEC);
     tp.in_is_frame = first ? 1 : 0;
     auto row_of = [&](const __half* w) { return (int)((w - m.dev_f16) / 128); };
     if (mode == EDGE_ENC_NODE) {
         const EncLayerW& e = m.enc[layer];
-        tp.P = plan_P(p, 0); tp.Pc = p.Pc16[0]; tp.n_w = 2;
-        tp.w_row[0] = row_of(e.W1b_h); tp.w_row[1] = row_of(e.W2_h); tp.b2 = e.b2;
+        tp.P16 = p.P16[0]; tp.n_w = 2;
+        tp.w_row[0] = row_of(e.W1b_h); tp.w_row[1] = row_of(e.W2_h); tp.b2h = e.b2_16;
     } else if (mode == EDGE_ENC_EDGE) {
         const EncLayerW& e = m.enc[layer];
-        tp.P = plan_P(p, 1); tp.Pc = p.Pc16[1]; tp.n_w = 3;
+        tp.P16 = p.P16[1]; tp.n_w = 3;
         tp.w_row[0] = row_of(e.W11b_h); tp.w_row[1] = row_of(e.W12_h); tp.w_row[2] = row_of(e.W13_h);
-        tp.b2 = e.b12; tp.b3 = e.b13;
-        tp.mod = mod_base + CB2_MOD_ENC_OFF(layer);
+        tp.b2h = e.b12_16; tp.b3 = e.b13;
+        const size_t row0 = (size_t)(mod_base - p.mod) / CB2_MOD_TOTAL;      // row of the current step (sampling) or of member 0 (forward)
+        tp.mod16 = p.mod16 + row0 * 768 + layer * 256;
+        tp.mod16_stride = mod_stride_b ? 768 : 0;
         tp.res = reinterpret_cast<const __half*>(first ? p.hE0 : p.hE);
     } else {
         const DecLayerW& d = m.dec[layer];
-        tp.P = plan_P(p, 0); tp.Pc = p.Pc16[0]; tp.n_w = 2;
-        tp.w_row[0] = row_of(d.W1b2_h); tp.w_row[1] = row_of(d.W2_h); tp.b2 = d.b2;
+        tp.P16 = p.P16[0]; tp.n_w = 2;
+        tp.w_row[0] = row_of(d.W1b2_h); tp.w_row[1] = row_of(d.W2_h); tp.b2h = d.b2_16;
     }
-    if (mode == EDGE_ENC_EDGE) {
-        const int grid = min(p.num_sms, (tp.n_tiles + 2) / 3);
-        edge_tc_kernel<3, EDGE_ENC_EDGE><<<grid, 3 * 128, tc_smem_bytes(3, 3), s>>>(maps, tp);
-    } else {
-        const int grid = min(p.num_sms, (tp.n_tiles + 3) / 4);
-        if (mode == EDGE_ENC_NODE) edge_tc_kernel<4, EDGE_ENC_NODE><<<grid, 4 * 128, tc_smem_bytes(4, 2), s>>>(maps, tp);
-        else edge_tc_kernel<4, EDGE_DEC><<<grid, 4 * 128, tc_smem_bytes(4, 2), s>>>(maps, tp);
-    }
+    const int grid = min(p.num_sms, (tp.n_tiles + 3) / 4);
+    if (mode == EDGE_ENC_NODE) edge_tc_kernel<EDGE_ENC_NODE><<<grid, CTA_THREADS, tc_smem_bytes(mode), s>>>(maps, tp);
+    else if (mode == EDGE_ENC_EDGE) edge_tc_kernel<EDGE_ENC_EDGE><<<grid, CTA_THREADS, tc_smem_bytes(mode), s>>>(maps, tp);
+    else edge_tc_kernel<EDGE_DEC><<<grid, CTA_THREADS, tc_smem_bytes(mode), s>>>(maps, tp);
     CB2_LAUNCH_CHECK();
     p.launches++;
     return 0;

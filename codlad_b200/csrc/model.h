@@ -20,6 +20,7 @@ struct EncLayerW {
     const float *Win_t, *bin, *Wout_t, *bout;
     const __half *W1b_h, *W2_h, *W11b_h, *W12_h, *W13_h;
     const __half *W1a_h, *W1c_h, *W11a_h, *W11c_h, *W3_h, *Win_h /* 4 blocks */, *Wout_h /* 4 blocks */;
+    const __half *b2_16, *b12_16;      // fp16 copies of the second-layer biases (tensor-core epilogues)
 };
 
 struct DecLayerW {
@@ -28,6 +29,7 @@ struct DecLayerW {
     const float *W2_t, *b2, *W3_t, *b3, *Win_t, *bin, *Wout_t, *bout;
     const __half *W1b2_h, *W2_h;
     const __half *W1a_h, *W1d_h, *W3_h, *Win_h /* 4 blocks */, *Wout_h /* 4 blocks */;
+    const __half* b2_16;
 };
 
 struct DenoiserModel {
@@ -43,6 +45,7 @@ struct DenoiserModel {
     const float *fin_w_t /* [128][6] */, *fin_b;
     float* dev_f32 = nullptr;
     __half* dev_f16 = nullptr;
+    __half* dev_vec16 = nullptr;
     int n_f16_blocks = 0;
 };
 
@@ -68,8 +71,10 @@ struct Plan {
     float* hV = nullptr;            // [NB*L, 128]
     float* hVenc = nullptr;         // [NB*L, 128]
     float* P = nullptr;             // [2][NB*L, 256] per-node halves of the edge MLPs' first layer: [own | gathered]
-    __half* Pc16[2] = {nullptr, nullptr};   // fp16 tier: [NB*L, 128] copy of the gathered half of each P buffer
+    __half* P16[2] = {nullptr, nullptr};    // fp16 tier: [NB*L, 256] = [own half + bias | gathered half] of the two first-layer splits
+    __half* mod16 = nullptr;                // fp16 tier: [mod_capacity, 3, 256] edge-stream adaLN: gate (1 + scale) | gate * shift
     int num_sms = 148;
+    unsigned long long* tc_trace = nullptr;   // debug: stage timestamps of one tensor-core edge pipeline ("tc_trace" buffer)
     float* silu_c = nullptr;        // [mod_capacity, 128] scratch of the timestep embedder
     float* S = nullptr;             // [NB*L, 128]  aggregated messages
     float* out6 = nullptr;          // [NB*L, 6]
@@ -93,7 +98,7 @@ struct Plan {
 int launch_knn(const float* X, const int* lengths, int F, int L, int K, float* D, int* idx, cudaStream_t s);
 int launch_edge_features(const DenoiserModel& m, const float* X, const int* lengths, const int* idx, const float* D,
                          int F, int L, int K, float* E_dbg, void* hE0, int precision, cudaStream_t s);
-int launch_timestep_mod(const DenoiserModel& m, const float* tvals, int n, float* scratch_silu_c, float* mod, cudaStream_t s);
+int launch_timestep_mod(const DenoiserModel& m, const float* tvals, int n, float* scratch_silu_c, float* mod, __half* mod16, cudaStream_t s);
 int launch_p_sample(const float* x, const float* out6, const float* noise, const float* coef_rows, const int* step_of_row,
                     int rows_per_b, int n_rows, int C, float* x_next, cudaStream_t s);
 float* plan_P(Plan& p, int which);

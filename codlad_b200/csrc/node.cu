@@ -54,11 +54,21 @@ __global__ void __launch_bounds__(128) adaln_table_kernel(const float* __restric
     mod[(size_t)n * CB2_MOD_TOTAL + col] = o;
 }
 
+// edge-stream adaLN of the three encoder layers in the form the tensor-core epilogue consumes:
+// mod16[n][l] = [gate3 (1 + scale3) | gate3 * shift3] as fp16 (protein_mpnn_utils.py:270)
+__global__ void __launch_bounds__(128) mod16_kernel(const float* __restrict__ mod, __half* __restrict__ mod16) {
+    const int n = blockIdx.x, l = blockIdx.y, c = threadIdx.x;
+    const float* m = mod + (size_t)n * CB2_MOD_TOTAL + CB2_MOD_ENC_OFF(l);
+    const float gate = m[1024 + c];
+    __half* o = mod16 + ((size_t)n * 3 + l) * 256;
+    o[c] = __float2half_rn(gate * (1.0f + m[896 + c]));
+    o[128 + c] = __float2half_rn(gate * m[768 + c]);
+}
+
 // ------------------------------------------------------------------ node update
 struct Proj {                // P[n] = [Wa h + ba | Wc h' (+ table[z])],  h' = h (+ h_enc)
     const float *Wa_t, *ba, *Wc_t, *table;
     float* out;              // [N, 256]
-    __half* out16;           // fp16 tier: [N, 128] copy of the gathered half (nullptr in the fp32 tier)
     int add_enc;             // 0: h' = h, 1: h' = h + hVenc[n], 2: h' = 2 h (this kernel is producing hVenc)
 };
 
@@ -252,7 +262,6 @@ __global__ void __launch_bounds__(128) node_update_kernel(NodeParams p) {
                     v += pj.table[z * 128 + c];
                 }
                 pj.out[(size_t)n * 256 + 128 + c] = v;
-                if (pj.out16 != nullptr) pj.out16[(size_t)n * 128 + c] = __float2half_rn(v);
             }
         }
     }
@@ -313,11 +322,15 @@ __global__ void p_sample_kernel(const float* __restrict__ x, const float* __rest
 
 }  // namespace
 
-int launch_timestep_mod(const DenoiserModel& m, const float* tvals, int n, float* scratch_silu_c, float* mod, cudaStream_t s) {
+int launch_timestep_mod(const DenoiserModel& m, const float* tvals, int n, float* scratch_silu_c, float* mod, __half* mod16, cudaStream_t s) {
     timestep_cond_kernel<<<n, 128, 0, s>>>(tvals, m.freqs, m.te_w0_t, m.te_b0, m.te_w2_t, m.te_b2, scratch_silu_c);
     CB2_LAUNCH_CHECK();
     adaln_table_kernel<<<dim3(n, CB2_MOD_TOTAL / 128), 128, 0, s>>>(scratch_silu_c, m.ada_w_t, m.ada_b, mod);
     CB2_LAUNCH_CHECK();
+    if (mod16 != nullptr) {
+        mod16_kernel<<<dim3(n, 3), 128, 0, s>>>(mod, mod16);
+        CB2_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -359,7 +372,7 @@ int launch_node_init(Plan& p, const float* x, const float* mod_base, int mod_str
     np.do_update = 0;
     np.x = x; np.xin_w_t = m.xin_w_t; np.xin_b = m.xin_b;
     np.n_proj = 1;
-    np.proj[0] = Proj{m.enc[0].W1a_t, m.enc[0].b1, m.enc[0].W1c_t, nullptr, plan_P(p, 0), p.Pc16[0], 0};
+    np.proj[0] = Proj{m.enc[0].W1a_t, m.enc[0].b1, m.enc[0].W1c_t, nullptr, plan_P(p, 0), 0};
     return node_launch(p, np, s);
 }
 
@@ -376,14 +389,14 @@ int launch_node_update(Plan& p, int phase, const float* mod_base, int mod_stride
         np.W3_t = e.W3_t; np.b3 = e.b3; np.Win_t = e.Win_t; np.bin = e.bin; np.Wout_t = e.Wout_t; np.bout = e.bout;
         np.mod = mod_base + CB2_MOD_ENC_OFF(phase);
         np.n_proj = 2;
-        np.proj[0] = Proj{e.W11a_t, e.b11, e.W11c_t, nullptr, plan_P(p, 1), p.Pc16[1], 0};          // this layer's edge update
+        np.proj[0] = Proj{e.W11a_t, e.b11, e.W11c_t, nullptr, plan_P(p, 1), 0};          // this layer's edge update
         if (phase < 2) {
             const EncLayerW& nx = m.enc[phase + 1];
-            np.proj[1] = Proj{nx.W1a_t, nx.b1, nx.W1c_t, nullptr, plan_P(p, 0), p.Pc16[0], 0};        // next layer's node message
+            np.proj[1] = Proj{nx.W1a_t, nx.b1, nx.W1c_t, nullptr, plan_P(p, 0), 0};        // next layer's node message
         } else {
             const DecLayerW& d = m.dec[0];
             np.write_enc = 1;
-            np.proj[1] = Proj{d.W1a_t, d.b1, d.W1d_t, d.TS, plan_P(p, 0), p.Pc16[0], 2};              // h_V + h_Venc = 2 h_V here
+            np.proj[1] = Proj{d.W1a_t, d.b1, d.W1d_t, d.TS, plan_P(p, 0), 2};              // h_V + h_Venc = 2 h_V here
         }
     } else {
         const int l = phase - 3;
@@ -394,7 +407,7 @@ int launch_node_update(Plan& p, int phase, const float* mod_base, int mod_stride
         if (l < 2) {
             const DecLayerW& nx = m.dec[l + 1];
             np.n_proj = 1;
-            np.proj[0] = Proj{nx.W1a_t, nx.b1, nx.W1d_t, nx.TS, plan_P(p, 0), p.Pc16[0], 1};
+            np.proj[0] = Proj{nx.W1a_t, nx.b1, nx.W1d_t, nx.TS, plan_P(p, 0), 1};
         } else {
             np.n_proj = 0;
             np.do_final = 1;

@@ -26,8 +26,7 @@ namespace {
 struct ProjTc {
     int wa_row, wc_row;          // weight blocks (rows of the packed fp16 weight tensor)
     const float *ba, *table;     // own-half bias; optional per-residue-type table added to the gathered half
-    float* out;                  // [N, 256] (only [:, :128] is written: the tensor-core edge kernels gather Pc16)
-    __half* out16;               // [N, 128]
+    __half* out16;               // [N, 256] fp16: [own half + bias | gathered half (+ table)]
     int add_enc;                 // 0: h' = h, 1: h' = h + hVenc, 2: h' = 2 h
 };
 
@@ -336,7 +335,12 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
                     for (int e = 0; e < 32; ++e) acc[e] += bb[e];
                     if (live) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) stg_f32x8(pj.out + (size_t)n * 256 + c * 32 + u * 8, acc + u * 8);
+                        for (int u = 0; u < 2; ++u) {
+                            uint32_t o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] = f2_to_h2(acc[u * 16 + e * 2], acc[u * 16 + e * 2 + 1]);
+                            stg256(pj.out16 + (size_t)n * 256 + c * 32 + u * 16, o);
+                        }
                     }
                     tmem_ld32(tmem_row + (2 * j + 1) * 128 + c * 32, acc);
                     if (pj.table != nullptr) {
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
                             uint32_t o[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) o[e] = f2_to_h2(acc[u * 16 + e * 2], acc[u * 16 + e * 2 + 1]);
-                            stg256(pj.out16 + (size_t)n * 128 + c * 32 + u * 16, o);
+                            stg256(pj.out16 + (size_t)n * 256 + 128 + c * 32 + u * 16, o);
                         }
                     }
                 }
@@ -443,7 +447,7 @@ int launch_node_init_tc(Plan& p, const float* x, cudaStream_t s) {
     np.do_update = 0;
     np.x = x; np.xin_w_t = m.xin_w_t; np.xin_b = m.xin_b;
     np.n_proj = 1;
-    np.proj[0] = ProjTc{row_of(m.enc[0].W1a_h), row_of(m.enc[0].W1c_h), m.enc[0].b1, nullptr, plan_P(p, 0), p.Pc16[0], 0};
+    np.proj[0] = ProjTc{row_of(m.enc[0].W1a_h), row_of(m.enc[0].W1c_h), m.enc[0].b1, nullptr, p.P16[0], 0};
     return node_tc_launch(p, np, s);
 }
 
@@ -462,14 +466,14 @@ int launch_node_update_tc(Plan& p, int phase, const float* mod_base, int mod_str
         np.b3 = e.b3; np.bin = e.bin; np.bout = e.bout;
         np.mod = mod_base + CB2_MOD_ENC_OFF(phase);
         np.n_proj = 2;
-        np.proj[0] = ProjTc{row_of(e.W11a_h), row_of(e.W11c_h), e.b11, nullptr, plan_P(p, 1), p.Pc16[1], 0};
+        np.proj[0] = ProjTc{row_of(e.W11a_h), row_of(e.W11c_h), e.b11, nullptr, p.P16[1], 0};
         if (phase < 2) {
             const EncLayerW& nx = m.enc[phase + 1];
-            np.proj[1] = ProjTc{row_of(nx.W1a_h), row_of(nx.W1c_h), nx.b1, nullptr, plan_P(p, 0), p.Pc16[0], 0};
+            np.proj[1] = ProjTc{row_of(nx.W1a_h), row_of(nx.W1c_h), nx.b1, nullptr, p.P16[0], 0};
         } else {
             const DecLayerW& d = m.dec[0];
             np.write_enc = 1;
-            np.proj[1] = ProjTc{row_of(d.W1a_h), row_of(d.W1d_h), d.b1, d.TS, plan_P(p, 0), p.Pc16[0], 2};
+            np.proj[1] = ProjTc{row_of(d.W1a_h), row_of(d.W1d_h), d.b1, d.TS, p.P16[0], 2};
         }
     } else {
         const int l = phase - 3;
@@ -481,7 +485,7 @@ int launch_node_update_tc(Plan& p, int phase, const float* mod_base, int mod_str
         if (l < 2) {
             const DecLayerW& nx = m.dec[l + 1];
             np.n_proj = 1;
-            np.proj[0] = ProjTc{row_of(nx.W1a_h), row_of(nx.W1d_h), nx.b1, nx.TS, plan_P(p, 0), p.Pc16[0], 1};
+            np.proj[0] = ProjTc{row_of(nx.W1a_h), row_of(nx.W1d_h), nx.b1, nx.TS, p.P16[0], 1};
         } else {
             np.n_proj = 0;
             np.do_final = 1;
