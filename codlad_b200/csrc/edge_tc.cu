@@ -5,13 +5,14 @@
 //
 //   * edge state h_E, activations and weights are fp16 (kind::f16 MMA, fp32 accumulation in TMEM).  fp16 rather
 //     than bf16: same tensor rate, 8x finer mantissa, and every operand here is LayerNorm/GELU-bounded.
-//   * one persistent CTA per SM = two independent 256-thread pipelines that share the layer weights resident in
-//     shared memory (SWIZZLE_128B, K-major, loaded once by TMA).  Each pipeline keeps TWO tiles in flight (two
-//     32 KB operand buffers, two 128-column TMEM accumulators) and interleaves their stages
-//     E1(0) E3(1) E2(0) E1(1) E3(0) E2(1) ..., so a tile's MMA / TMA latency is covered by the other tile's epilogue.
+//   * one persistent CTA per SM: 16 epilogue warps + one MMA-issuing lane + one TMA-issuing lane.  The layer weights
+//     stay resident in shared memory (SWIZZLE_128B, K-major, loaded once by TMA); FOUR tiles are in flight (four
+//     32 KB operand buffers, four 128-column TMEM accumulators).  The epilogue warps run the stages round-robin
+//     E1(0..3) E2(0..3) E3(0..3), so between two stages of a tile the other three tiles' stages run and cover its
+//     MMA / TMA latency; the control lanes issue every MMA and TMA the moment its inputs are ready.
 //     A tile = NPT whole nodes (NPT*K <= 128 neighbour rows) of one ensemble member: the neighbour sum is tile-local.
-//   * thread (row r, column half h): the two warpgroups of a pipeline split the 128 accumulator columns of every row
-//     (both can address TMEM lane r), which halves the per-tile epilogue latency.
+//   * epilogue thread (row r, column quarter cq): the four warps that can address a TMEM lane quarter split the 128
+//     accumulator columns of every row, so all 16 warps work on ONE tile stage at a time (the stages are MUFU-bound).
 //   * per tile: TMA loads the h_E rows (contiguous in HBM) into a swizzled K-major A tile -> MMA 1 (W?b h_E) ->
 //     E1: accumulator from TMEM, + own half Pa[i] (L1 broadcast) + gathered half Pc[j] (fp16, 256-bit loads from L2),
 //     GELU, fp16 activation back into the same smem tile -> MMA 2 -> E2 (+b, GELU) ->
@@ -75,35 +76,34 @@ __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
     const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
     return __hfma2(h, as_h2(t), h);
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the 256 epilogue threads only
 
-struct TileMeta {            // per-thread view of a tile (kept small: four of them live in registers)
-    int tile;                // global tile index (>= n_tiles: this slot has run out of work)
-    int nv;                  // valid nodes in the tile
-    int in_row0;             // first edge row of the tile in the input tensor (ENC_EDGE residual)
-    int node0;               // first node (member indexing)
-    uint32_t keep;           // 0xffffffff if this row takes part in the neighbour sum
-    int pa_node;             // this thread's node          -> own half      P16[pa_node][c0 ...]
-    int pc_node;             // this thread's neighbour     -> gathered half P16[pc_node][128 + c0 ...]
-    int member;              // ENC_EDGE: row of mod16
-};
-
-constexpr int EPI_THREADS = 256;                // thread (row r, column half h): two warpgroups split the accumulator columns
+constexpr int EPI_THREADS = 512;                // thread (row r, column quarter cq)
 constexpr int CTA_THREADS = EPI_THREADS + 64;   // + two control warps (one lane each): MMA issue, TMA issue
 constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 KB operand buffer + 128 TMEM columns each)
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the epilogue threads only
+
+// per-thread view of a tile, packed into two registers (four of them are live; they rotate so that the stage code
+// exists once):  a = node0 | q_of_row << 26 | nv << 28 ;  b = neighbour node | keep << 31
+struct TileMeta { uint32_t a, b; };
+__device__ __forceinline__ int meta_node0(const TileMeta& m) { return (int)(m.a & 0x3ffffffu); }
+__device__ __forceinline__ int meta_q(const TileMeta& m) { return (int)((m.a >> 26) & 3u); }
+__device__ __forceinline__ int meta_nv(const TileMeta& m) { return (int)(m.a >> 28); }
+__device__ __forceinline__ int meta_pc_node(const TileMeta& m) { return (int)(m.b & 0x7fffffffu); }
+__device__ __forceinline__ uint32_t meta_keep(const TileMeta& m) { return (uint32_t)((int)m.b >> 31); }
 
 template <int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int N_W = MODE == EDGE_ENC_EDGE ? 3 : 2;
-    // layout: [weights N_W x 32 KB][4 tile slots x 32 KB][indicator 4 KB | LN exchange 1 KB][barriers]
+    // layout: [weights N_W x 32 KB][4 tile slots x 32 KB][indicator 4 KB | LN statistics 1 KB][barriers]
     unsigned char* sW = smem;
     unsigned char* sT = sW + N_W * TILE_BYTES;
     unsigned char* sAux = sT + 4 * TILE_BYTES;
     unsigned char* sInd = sAux;                                                   // ENC_NODE / DEC
-    float2* sXchg = reinterpret_cast<float2*>(sAux);                              // ENC_EDGE: [128 rows]
-    // barriers: [0] weights; per tile slot g: [1+3g] load (TMA tx), [2+3g] acc (MMA commit), [3+3g] epi (256 arrivals)
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sAux + (MODE == EDGE_ENC_EDGE ? 1024 : IND_BYTES));
+    unsigned long long* sStat = reinterpret_cast<unsigned long long*>(sAux);      // ENC_EDGE: [128 rows][sum, sum of squares], fixed point
+    // barriers: [0] weights; per tile slot g: [1+3g] load (TMA tx), [2+3g] acc (MMA commit), [3+3g] epi (512 arrivals); [13+g] go
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sAux + (MODE == EDGE_ENC_EDGE ? 2048 : IND_BYTES));
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 17);
 
     const int tid = threadIdx.x;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         for (int g = 0; g < 4; ++g) {
             mbar_init(smem_u32(&sBar[1 + 3 * g]), 1);
             mbar_init(smem_u32(&sBar[2 + 3 * g]), 1);
-            mbar_init(smem_u32(&sBar[3 + 3 * g]), 256);
+            mbar_init(smem_u32(&sBar[3 + 3 * g]), EPI_THREADS);
             mbar_init(smem_u32(&sBar[13 + g]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             const uint32_t off = (uint32_t)((c16 >> 3) * (16 * 128) + q * 128 + (((c16 & 7) ^ (q & 7)) << 4));
             *reinterpret_cast<uint4*>(sInd + off) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+    } else if (tid < 256) {
+        sStat[tid] = 0ull;
     }
     fence_async_smem();
     tc_fence_before();
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 
     if (tid >= EPI_THREADS) {
         // =========================================================================== control warps (one lane each)
-        // warp 8 issues every MMA, warp 9 every TMA, in the order the epilogue warps consume them: the epilogue
+        // warp 16 issues every MMA, warp 17 every TMA, in the order the epilogue warps consume them: the epilogue
         // threads never execute issue code and a tile's MMA / TMA latency is covered by the other tiles' epilogues.
         // (MMA and TMA issue are split because a thread's tcgen05.mma stalls behind its own in-flight bulk copies.)
         auto T_u32 = [&](int g) { return smem_u32(sT + g * TILE_BYTES); };
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             if (MODE == EDGE_ENC_EDGE) tma_store_wait_all();
         } else if (tid == EPI_THREADS) {
             // ------------------------------------------------------------------ MMA thread
-            uint32_t ph_load = 0, ph_epi = 0;
+            uint32_t ph_epi = 0;
             auto issue_mma = [&](int g, int w_slot) {                 // 128x128x128 GEMM, A = tile g, B = weight slot
                 tc_fence_after();
 #pragma unroll
@@ -251,220 +253,196 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 if (MODE == EDGE_ENC_EDGE && n - 1 < n_next) { mbar_wait(bar_load(n - 1), next_parity); issue_mma(n - 1, 0); }
                 ph_epi ^= 1;
             }
-            (void)ph_load;
         }
     } else {
         // =========================================================================== epilogue threads
-        const int half = tid >> 7, r = tid & 127, quarter = (tid >> 5) & 3;
-        const int c0 = half * 64;                                      // this thread's 64 accumulator columns
-        auto T_of = [&](int s) { return sT + s * TILE_BYTES; };
-        auto bar_acc = [&](int s) { return smem_u32(&sBar[2 + 3 * s]); };
-        auto bar_epi = [&](int s) { return smem_u32(&sBar[3 + 3 * s]); };
-        auto tmem_row = [&](int s) { return tmem_base + (uint32_t)(s * 128) + ((uint32_t)(quarter * 32) << 16); };
-        auto done = [&](int s) { fence_async_smem(); tc_fence_before(); mbar_arrive(bar_epi(s)); };     // (mark(6) follows in the callers)
+        const int warp = tid >> 5, quarter = warp & 3, cq = warp >> 2, r = quarter * 32 + (tid & 31);
+        const int c0 = cq * 32;                                        // this thread's 32 accumulator columns
+        const int q_of_r = r / K;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
 
-        // per-tile metadata (its global loads are issued a full tile ahead of their use)
+        // metadata of tile `tile` for this thread (global loads; consumed a full round later)
         auto load_meta = [&](int tile) {
-            TileMeta m{};
-            m.tile = tile;
+            TileMeta m{0u, 0u};
             if (tile >= p.n_tiles) return m;
             const int b = tile / p.tiles_per_member;
             const int i0 = (tile - b * p.tiles_per_member) * NPT;
-            m.nv = min(NPT, p.L - i0);
+            const int nv = min(NPT, p.L - i0);
             const int f = __ldg(p.frame_of + b);                        // tiny arrays: L1 hits
             const int len = __ldg(p.lengths + f);
-            m.node0 = b * p.L + i0;
-            m.in_row0 = ((p.in_is_frame ? f : b) * p.L + i0) * K;
-            const int q = r / K;
             int j = 0, qq = 0;
-            m.keep = 0u;
-            if (q < m.nv) {
-                const int i = i0 + q;
-                qq = q;
-                j = __ldg(p.nbr_idx + ((size_t)f * p.L + i) * K + (r - q * K));
-                m.keep = (MODE == EDGE_DEC || (i < len && j < len)) ? 0xffffffffu : 0u;
+            uint32_t keep = 0u;
+            if (q_of_r < nv) {
+                const int i = i0 + q_of_r;
+                qq = q_of_r;
+                j = __ldg(p.nbr_idx + ((size_t)f * p.L + i) * K + (r - q_of_r * K));
+                keep = (MODE == EDGE_DEC || (i < len && j < len)) ? 1u : 0u;
             }
-            m.pa_node = m.node0 + qq;
-            m.pc_node = b * p.L + j;
-            m.member = b;
+            m.a = (uint32_t)(b * p.L + i0) | ((uint32_t)qq << 26) | ((uint32_t)nv << 28);
+            m.b = (uint32_t)(b * p.L + j) | (keep << 31);
             return m;
         };
-        unsigned long long* trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
-        int n_trace = 0;
-        auto mark = [&](int ev, int s) {
-            if (trace != nullptr && n_trace < 1000) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                trace[1 + n_trace] = (t << 8) | (unsigned long long)((ev << 2) | s);
-                trace[0] = (unsigned long long)(++n_trace);
-            }
+        auto ld_pc = [&](const TileMeta& m, uint32_t (&pc)[16]) {       // this thread's 32 gathered halves of Pc[j]
+            const __half* src = p.P16 + (size_t)meta_pc_node(m) * 256 + 128 + c0;
+            ldg256(src, *reinterpret_cast<uint32_t(*)[8]>(&pc[0]));
+            ldg256(src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[8]));
         };
-        TileMeta meta[NSLOT];
-        uint32_t ph_acc[NSLOT] = {0, 0, 0, 0};
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) meta[s] = load_meta(blockIdx.x * NSLOT + s);
+        // packed-half store of 16 consecutive columns [c0 + g16*16, +16) of row r
+        auto st16 = [&](unsigned char* T, int g16, const uint32_t (&o)[8]) {
+            *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+        };
 
-        // ---- E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile ----
-        auto epi1 = [&](int s) {
-            const TileMeta& m = meta[s];
-            unsigned char* T = T_of(s);
-            uint32_t pc[32], pa[32];                                     // this thread's 64 gathered / own halves: loads in flight
-#pragma unroll                                                          // while the MMA completes
-            for (int q = 0; q < 4; ++q) ldg256(p.P16 + (size_t)m.pc_node * 256 + 128 + c0 + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[q * 8]));
+        TileMeta m0 = load_meta(blockIdx.x * NSLOT + 0), m1 = load_meta(blockIdx.x * NSLOT + 1),
+                 m2 = load_meta(blockIdx.x * NSLOT + 2), m3 = load_meta(blockIdx.x * NSLOT + 3);
+        auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
+        uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
+        uint32_t pcA[16], pcB[16];                                      // gathered halves, double buffered one stage ahead
+        ld_pc(m0, pcA);
+
+        for (int t0 = blockIdx.x * NSLOT; t0 < p.n_tiles; t0 += tile_stride) {
+            const int n = min(NSLOT, p.n_tiles - t0);                   // live slots of this round
+            // ================= E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile
+            auto epi1 = [&](int s, const uint32_t (&pc)[16]) {
+                unsigned char* T = sT + s * TILE_BYTES;
+                uint32_t pa[16];
+                const __half* pa_src = p.P16 + (size_t)(meta_node0(m0) + meta_q(m0)) * 256 + c0;
+                ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
+                ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
+                mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
+                tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ldg256(p.P16 + (size_t)m.pa_node * 256 + c0 + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[q * 8]));
-            mark(0, s);
-            mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
-            tc_fence_after();
-            mark(1, s);
+                for (int g16 = 0; g16 < 2; ++g16) {
+                    float acc[16];
+                    tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
+                    uint32_t o[8];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float acc[32];
-                tmem_ld32(tmem_row(s) + c0 + c * 32, acc);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(pa[c * 16 + u * 4 + e])),
-                                                  as_h2(pc[c * 16 + u * 4 + e]));
+                    for (int e = 0; e < 8; ++e) {
+                        const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(pa[g16 * 8 + e])), as_h2(pc[g16 * 8 + e]));
                         o[e] = as_u32(gelu_h2(x));
                     }
-                    *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    st16(T, g16, o);
                 }
+                fence_async_smem(); tc_fence_before(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));
+            };
+#pragma unroll 1
+            for (int s2 = 0; s2 < NSLOT; s2 += 2) {
+                if (s2 < n) { if (s2 + 1 < n) ld_pc(m1, pcB); epi1(s2, pcA); }
+                rotate();
+                if (s2 + 1 < n) { if (s2 + 2 < n) ld_pc(m1, pcA); epi1(s2 + 1, pcB); }
+                rotate();
             }
-            done(s);
-            mark(6, s);
-        };
-        // ---- E2: GELU(acc + b2) (masked rows -> 0 for the reduction) -> fp16 tile ----
-        auto epi2 = [&](int s) {
-            const TileMeta& m = meta[s];
-            unsigned char* T = T_of(s);
-            const uint32_t keep = MODE == EDGE_ENC_EDGE ? 0xffffffffu : m.keep;
-            uint32_t b2r[32];                                            // second-layer bias of this thread's 64 columns (fp16 pairs)
+            ph ^= 1;
+            // ================= E2: GELU(acc + b2) (masked rows -> 0 for the reduction) -> fp16 tile
+#pragma unroll 1
+            for (int s = 0; s < NSLOT; ++s) {
+                if (s < n) {
+                    unsigned char* T = sT + s * TILE_BYTES;
+                    const uint32_t keep = MODE == EDGE_ENC_EDGE ? 0xffffffffu : meta_keep(m0);
+                    uint32_t bb[16];
+                    ldg256(p.b2h + c0, *reinterpret_cast<uint32_t(*)[8]>(&bb[0]));
+                    ldg256(p.b2h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&bb[8]));
+                    mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
+                    tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ldg256(p.b2h + c0 + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&b2r[q * 8]));
-            mark(2, s);
-            mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
-            tc_fence_after();
-            mark(3, s);
+                    for (int g16 = 0; g16 < 2; ++g16) {
+                        float acc[16];
+                        tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
+                        uint32_t o[8];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t* bb = b2r + c * 16;
-                float acc[32];
-                tmem_ld32(tmem_row(s) + c0 + c * 32, acc);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __half2 x = __hadd2(as_h2(pack_sat(acc[u * 8 + e * 2], acc[u * 8 + e * 2 + 1])), as_h2(bb[u * 4 + e]));
-                        o[e] = as_u32(gelu_h2(x)) & keep;
-                    }
-                    *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-            done(s);
-            mark(6, s);
-        };
-        // ---- E3: finish the tile, fetch the metadata of the slot's next tile ----
-        auto epi3 = [&](int s) {
-            const TileMeta m = meta[s];
-            unsigned char* T = T_of(s);
-            const int next_tile = m.tile + tile_stride;
-            if (MODE != EDGE_ENC_EDGE) {
-                meta[s] = load_meta(next_tile);
-                mark(4, s);
-                mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
-                tc_fence_after();
-                mark(5, s);
-                if (half == 0) {
-                    float s4[4];
-                    tmem_ld4(tmem_row(s), s4);                // lane = output column, 4 columns = nodes of the tile
-#pragma unroll
-                    for (int q = 0; q < MAX_NPT; ++q)
-                        if (q < m.nv) p.S[((size_t)m.node0 + q) * 128 + r] = s4[q];
-                }
-                done(s);                                      // accumulator drained: the slot's next MMA 1 may start
-            } else {
-                const __half* res_row = p.res + ((size_t)m.in_row0 + (r < m.nv * K ? r : 0)) * 128 + c0;
-                uint32_t rs[32];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) ldg256_coherent(res_row + q * 16, *reinterpret_cast<uint32_t(*)[8]>(&rs[q * 8]));
-                mark(4, s);
-                mbar_wait(bar_acc(s), ph_acc[s]); ph_acc[s] ^= 1;
-                tc_fence_after();
-                mark(5, s);
-                // pass A (fp32): v = residual + acc + b13, partial row statistics; v is parked as fp16 in the tile
-                float sum = 0.f, sq = 0.f;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float acc[32];
-                    tmem_ld32(tmem_row(s) + c0 + c * 32, acc);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint32_t o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int col = u * 8 + e * 2;
-                            const float2 rr = h2_to_f2(rs[c * 16 + u * 4 + e]);
-                            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b3 + c0 + c * 32 + col));
-                            const float v0 = rr.x + (acc[col] + bb.x), v1 = rr.y + (acc[col + 1] + bb.y);
-                            sum += v0 + v1;
-                            sq = fmaf(v0, v0, fmaf(v1, v1, sq));
-                            o[e] = pack_sat(v0, v1);
+                        for (int e = 0; e < 8; ++e) {
+                            const __half2 x = __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(bb[g16 * 8 + e]));
+                            o[e] = as_u32(gelu_h2(x)) & keep;
                         }
-                        *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c * 4 + u)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        st16(T, g16, o);
+                    }
+                    fence_async_smem(); tc_fence_before(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));
+                }
+                rotate();
+            }
+            ph ^= 1;
+            // ================= E3: finish the tile; fetch the metadata (and the first Pc) of the slot's next tile
+#pragma unroll 1
+            for (int s = 0; s < NSLOT; ++s) {
+                if (s < n) {
+                    const TileMeta m = m0;
+                    m0 = load_meta(t0 + tile_stride + s);
+                    if (MODE != EDGE_ENC_EDGE) {
+                        mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
+                        tc_fence_after();
+                        if (cq == 0) {
+                            float s4[4];
+                            tmem_ld4(tmem_lane + (uint32_t)(s * 128), s4);      // lane = output column, 4 columns = nodes of the tile
+                            const int nv = meta_nv(m);
+#pragma unroll
+                            for (int q = 0; q < MAX_NPT; ++q)
+                                if (q < nv) p.S[((size_t)meta_node0(m) + q) * 128 + r] = s4[q];
+                        }
+                        tc_fence_before(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));     // accumulator drained: the slot's next MMA 1 may start
+                    } else {
+                        unsigned char* T = sT + s * TILE_BYTES;
+                        const int node0 = meta_node0(m), bmem = node0 / p.L;
+                        const int in_row0 = p.in_is_frame ? (__ldg(p.frame_of + bmem) * p.L + (node0 - bmem * p.L)) * K : node0 * K;
+                        const __half* res_row = p.res + ((size_t)in_row0 + (r < meta_nv(m) * K ? r : 0)) * 128 + c0;
+                        uint32_t rs[16];
+                        ldg256_coherent(res_row, *reinterpret_cast<uint32_t(*)[8]>(&rs[0]));
+                        ldg256_coherent(res_row + 16, *reinterpret_cast<uint32_t(*)[8]>(&rs[8]));
+                        mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
+                        tc_fence_after();
+                        // pass A (fp32): v = residual + acc + b13, partial row statistics; v is parked as fp16 in the tile
+                        float sum = 0.f, sq = 0.f;
+#pragma unroll
+                        for (int g16 = 0; g16 < 2; ++g16) {
+                            float acc[16];
+                            tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
+                            uint32_t o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 rr = h2_to_f2(rs[g16 * 8 + e]);
+                                const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b3 + c0 + g16 * 16 + e * 2));
+                                const float v0 = rr.x + (acc[e * 2] + bb.x), v1 = rr.y + (acc[e * 2 + 1] + bb.y);
+                                sum += v0 + v1;
+                                sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+                                o[e] = pack_sat(v0, v1);
+                            }
+                            st16(T, g16, o);
+                        }
+                        // row statistics: the four column quarters of a row accumulate in shared memory.  64-bit fixed point
+                        // (2^-20 / 2^-16 resolution) keeps the sum associative, i.e. the result independent of arrival order.
+                        unsigned long long* st = sStat + r * 2;
+                        epi_sync();                                   // the previous stage's re-zeroing is complete
+                        atomicAdd(st, (unsigned long long)__float2ll_rn(sum * 1048576.0f));
+                        atomicAdd(st + 1, (unsigned long long)__float2ll_rn(sq * 65536.0f));
+                        tc_fence_before();
+                        epi_sync();
+                        const float tsum = (float)(long long)st[0] * (1.0f / 1048576.0f), tsq = (float)(long long)st[1] * (1.0f / 65536.0f);
+                        const float mean = tsum * (1.0f / 128.0f);
+                        const float rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
+                        epi_sync();
+                        if (cq == 0) { st[0] = 0ull; st[1] = 0ull; }
+                        const __half2 rstd2 = __float2half2_rn(rstd), mean2 = __float2half2_rn(mean);
+                        const __half* mod_row = p.mod16 + (size_t)bmem * p.mod16_stride + c0;
+                        // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
+#pragma unroll
+                        for (int c16 = 0; c16 < 4; ++c16) {
+                            uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16));
+                            const uint4 vv = *slot;
+                            const uint4 av = __ldg(reinterpret_cast<const uint4*>(mod_row + c16 * 8));
+                            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(mod_row + 128 + c16 * 8));
+                            const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w}, a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                            uint32_t o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
+                            *slot = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                        fence_async_smem(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));   // tile complete: the TMA lane stores it and reloads the slot
                     }
                 }
-                // row statistics: the two column halves of a row live in different warpgroups
-                float2* xr = sXchg + r;
-                if (half == 1) *xr = make_float2(sum, sq);
-                epi_sync();
-                float mean = 0.f, rstd = 0.f;
-                if (half == 0) {
-                    const float2 o = *xr;
-                    sum += o.x; sq += o.y;
-                    mean = sum * (1.0f / 128.0f);
-                    rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
-                    *xr = make_float2(mean, rstd);
-                }
-                meta[s] = load_meta(next_tile);
-                epi_sync();
-                if (half == 1) { const float2 o = *xr; mean = o.x; rstd = o.y; }
-                const __half2 rstd2 = __float2half2_rn(rstd), mean2 = __float2half2_rn(mean);
-                const __half* mod_row = p.mod16 + (size_t)m.member * p.mod16_stride;
-                // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
-#pragma unroll
-                for (int c16 = 0; c16 < 8; ++c16) {
-                    uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16));
-                    const uint4 vv = *slot;
-                    const uint4 av = __ldg(reinterpret_cast<const uint4*>(mod_row + c0 + c16 * 8));
-                    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(mod_row + 128 + c0 + c16 * 8));
-                    const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w}, a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
-                    *slot = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                done(s);                                      // tile complete: the control warp stores it and reloads the slot
+                rotate();
             }
-            mark(6, s);
-        };
-
-        // the slots advance in lock step (a slot that has run out of tiles is skipped): between two stages of a
-        // tile the other three tiles' stages run, which is what hides the MMA / TMA latency
-        while (meta[0].tile < p.n_tiles) {             // tiles are dealt in slot order, so slot 0 is the last to run dry
-            bool on[NSLOT];
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) on[s] = meta[s].tile < p.n_tiles;
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) if (on[s]) epi1(s);
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) if (on[s]) epi2(s);
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) if (on[s]) epi3(s);
+            ph ^= 1;
+            ld_pc(m0, pcA);                                             // first E1 of the next round
         }
     }
     tc_fence_before();
@@ -474,7 +452,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 
 size_t tc_smem_bytes(int mode) {
     const int n_w = mode == EDGE_ENC_EDGE ? 3 : 2;
-    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 1024 : IND_BYTES) + 17 * 8 + 16;
+    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 2048 : IND_BYTES) + 17 * 8 + 16;
 }
 
 }  // namespace
