@@ -44,6 +44,7 @@ struct TcMaps {
 struct TcParams {
     int L, K, NPT, tiles_per_member, n_tiles;
     int in_is_frame;                 // layer 0 of the encoder reads h_E0 (indexed by frame)
+    int single_frame;                // F == 1: every member uses frame 0 (no frame_of lookup on the metadata path)
     int w_row[3];                    // first row of each weight block in the packed weight tensor
     int n_w;                         // 2 (ENC_NODE / DEC) or 3 (ENC_EDGE)
     const __half* P16;               // [N, 256] fp16: [own half Wa h_V_i + b1 | gathered half Wc h_V_j (+ decoder table)]
@@ -58,25 +59,6 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// packed-half helpers of the epilogues
-__device__ __forceinline__ uint32_t pack_sat(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-// erf-GELU ~= 0.5 x (1 + tanh(x (a + b x^2))) on two fp16 values (coefficients refitted, see gelu_fast)
-__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
-    const __half2 x2 = __hmul2(x, x);
-    const __half2 pl = __hfma2(x2, __float2half2_rn(0.03470094f), __float2half2_rn(0.80015698f));
-    const __half2 u = __hmul2(x, pl);
-    uint32_t t;
-    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(as_u32(u)));
-    const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
-    return __hfma2(h, as_h2(t), h);
-}
-
 constexpr int EPI_THREADS = 512;                // thread (row r, column quarter cq)
 constexpr int CTA_THREADS = EPI_THREADS + 64;   // + two control warps (one lane each): MMA issue, TMA issue
 constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 KB operand buffer + 128 TMEM columns each)
@@ -259,6 +241,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         const int warp = tid >> 5, quarter = warp & 3, cq = warp >> 2, r = quarter * 32 + (tid & 31);
         const int c0 = cq * 32;                                        // this thread's 32 accumulator columns
         const int q_of_r = r / K;
+        const int len0 = __ldg(p.lengths);                             // length of frame 0 (the only frame of an ensemble plan)
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
 
         // metadata of tile `tile` for this thread (global loads; consumed a full round later)
@@ -268,8 +251,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             const int b = tile / p.tiles_per_member;
             const int i0 = (tile - b * p.tiles_per_member) * NPT;
             const int nv = min(NPT, p.L - i0);
-            const int f = __ldg(p.frame_of + b);                        // tiny arrays: L1 hits
-            const int len = __ldg(p.lengths + f);
+            const int f = p.single_frame ? 0 : __ldg(p.frame_of + b);    // (dependent loads only for multi-frame plans)
+            const int len = p.single_frame ? len0 : __ldg(p.lengths + f);
             int j = 0, qq = 0;
             uint32_t keep = 0u;
             if (q_of_r < nv) {
@@ -281,6 +264,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             m.a = (uint32_t)(b * p.L + i0) | ((uint32_t)qq << 26) | ((uint32_t)nv << 28);
             m.b = (uint32_t)(b * p.L + j) | (keep << 31);
             return m;
+        };
+        auto prefetch_pa = [&](const TileMeta& m) {                     // pull the own-half segment of the next stage into L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P16 + (size_t)(meta_node0(m) + meta_q(m)) * 256 + c0));
         };
         auto ld_pc = [&](const TileMeta& m, uint32_t (&pc)[16]) {       // this thread's 32 gathered halves of Pc[j]
             const __half* src = p.P16 + (size_t)meta_pc_node(m) * 256 + 128 + c0;
@@ -327,9 +313,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             };
 #pragma unroll 1
             for (int s2 = 0; s2 < NSLOT; s2 += 2) {
-                if (s2 < n) { if (s2 + 1 < n) ld_pc(m1, pcB); epi1(s2, pcA); }
+                if (s2 < n) { if (s2 + 1 < n) { ld_pc(m1, pcB); prefetch_pa(m1); } epi1(s2, pcA); }
                 rotate();
-                if (s2 + 1 < n) { if (s2 + 2 < n) ld_pc(m1, pcA); epi1(s2 + 1, pcB); }
+                if (s2 + 1 < n) { if (s2 + 2 < n) { ld_pc(m1, pcA); prefetch_pa(m1); } epi1(s2 + 1, pcB); }
                 rotate();
             }
             ph ^= 1;
@@ -443,6 +429,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             }
             ph ^= 1;
             ld_pc(m0, pcA);                                             // first E1 of the next round
+            prefetch_pa(m0);
         }
     }
     tc_fence_before();
@@ -493,6 +480,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     tp.trace = p.tc_trace;
     const bool first = (layer == 0 && mode != EDGE_DEC);
     tp.in_is_frame = first ? 1 : 0;
+    tp.single_frame = p.F == 1 ? 1 : 0;
     auto row_of = [&](const __half* w) { return (int)((w - m.dev_f16) / 128); };
     if (mode == EDGE_ENC_NODE) {
         const EncLayerW& e = m.enc[layer];

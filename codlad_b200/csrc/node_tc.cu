@@ -1,9 +1,10 @@
 // tcgen05 tier of the per-node kernels (same maths as node.cu; reference models/protein_mpnn_utils.py:247-259,
 // :307-317, models/latent_model.py:21-35,214, diffusion_and_flow/gaussian_diffusion.py:303-318,345-351,440-446).
 //
-// One CTA = one tile of 128 nodes.  Warps 0-3 are the epilogue warps (thread = node row = TMEM lane; every
-// LayerNorm / modulate / FinalLayer / p_sample reduction is thread-local because a thread owns a whole row);
-// warp 4 is the control warp: one lane streams the layer's fp16 weight blocks through four 32 KB shared-memory
+// One CTA = one tile of 128 nodes.  Warps 0-15 are the epilogue warps: thread (row r, column quarter cq) owns 32 of the
+// 128 columns of its node row (the four warps that can address a TMEM lane quarter split the columns); LayerNorm
+// row statistics are combined across the four quarters with order-independent fixed-point shared-memory atomics.
+// Warp 16 is the control warp: one lane streams the layer's fp16 weight blocks through four 32 KB shared-memory
 // slots with TMA and issues the tcgen05 MMAs.  The node kernels are latency chains (W3 -> LN -> FFN -> LN ->
 // projections), so the CTA alternates strictly between an MMA phase and an epilogue phase:
 //
@@ -81,23 +82,29 @@ __device__ __forceinline__ void store_row_chunk(unsigned char* tile, int r, int 
     }
 }
 
-__global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__ CUtensorMap wmap, const NodeTcParams p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+constexpr int NODE_EPI_THREADS = 512;
+
+__device__ __forceinline__ void node_epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const __grid_constant__ CUtensorMap wmap, const NodeTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* hA = smem;                         // current node state as the A operand
     unsigned char* mid0 = hA + TILE_BYTES;            // FFN hidden block / h' of the decoder projections
     unsigned char* mid1 = mid0 + TILE_BYTES;
     unsigned char* sW = mid1 + TILE_BYTES;            // 4 weight slots
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sW + 4 * TILE_BYTES);      // [0] weights full, [1] mma done, [2] activations ready
+    unsigned long long* sStat = reinterpret_cast<unsigned long long*>(sW + 4 * TILE_BYTES);   // [128 rows][sum, sum of squares], fixed point
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sStat + 256);              // [0] weights full, [1] mma done, [2] activations ready
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     const uint32_t bar_full = smem_u32(&sBar[0]), bar_mma = smem_u32(&sBar[1]), bar_act = smem_u32(&sBar[2]);
     if (tid == 0) {
-        mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_act, 128);
+        mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_act, NODE_EPI_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (tid < 256) sStat[tid] = 0ull;
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(sTmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
     constexpr uint32_t IDESC = umma_idesc(128, 128, 0, 0);
     const int n_phases = (p.do_update ? 4 : 0) + (p.n_proj > 0 ? 1 : 0);
 
-    if (warp == 4) {
+    if (warp == 16) {
         // ------------------------------------------------------------------ control warp
         if (lane == 0) {
             uint32_t ph_full = 0, ph_mma = 0, ph_act = 0;
@@ -154,11 +161,11 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps: thread = node row
-        const int r = tid;
+        // ------------------------------------------------------------------ epilogue warps: thread = (node row, 32 columns)
+        const int quarter = warp & 3, cq = warp >> 2, r = quarter * 32 + lane, c0 = cq * 32;
         const int n = blockIdx.x * 128 + r;
         const bool live = n < p.N;
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
         uint32_t ph_mma = 0;
         int b = 0, zres = 0;
         float mk = 0.f, cnt = (float)p.K;
@@ -178,62 +185,69 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
                 cnt = (float)cn;
             }
         }
-        const float* m = p.mod + (size_t)b * p.mod_stride;
-        float v[128];                                   // this row's state, fp32, register resident
+        const float* m = p.mod + (size_t)b * p.mod_stride + c0;
+        float v[32];                                    // this thread's 32 columns of the row state, fp32
         auto publish = [&]() { fence_async_smem(); tc_fence_before(); mbar_arrive(bar_act); };
         auto wait_mma = [&]() { mbar_wait(bar_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); };
-        // per-row LayerNorm statistics of v (no affine, eps 1e-6)
-        auto ln_stats = [&](float& mean, float& rstd) {
-            float s = 0.f;
+        auto store16 = [&](unsigned char* tile, int g16, const float* x) {     // 16 columns [c0 + 16 g16, +16) of row r as fp16
+            uint32_t o[8];
 #pragma unroll
-            for (int c = 0; c < 128; ++c) s += v[c];
-            mean = s * (1.0f / 128.0f);
-            float q = 0.f;
+            for (int e = 0; e < 8; ++e) o[e] = f2_to_h2(x[e * 2], x[e * 2 + 1]);
+            *reinterpret_cast<uint4*>(tile + tile_off(r, (c0 >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(tile + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+        };
+        // LayerNorm statistics of the full row (no affine, eps 1e-6): the four column quarters combine their partial sums
+        // in shared memory with 64-bit fixed-point atomics (associative -> the result does not depend on arrival order)
+        auto row_stats = [&](float& mean, float& rstd) {
+            float sum = 0.f, sq = 0.f;
 #pragma unroll
-            for (int c = 0; c < 128; ++c) { const float d = v[c] - mean; q = fmaf(d, d, q); }
-            rstd = rsqrtf(q * (1.0f / 128.0f) + 1e-6f);
+            for (int c = 0; c < 32; ++c) { sum += v[c]; sq = fmaf(v[c], v[c], sq); }
+            unsigned long long* st = sStat + r * 2;
+            node_epi_sync();                            // the previous use has been re-zeroed
+            atomicAdd(st, (unsigned long long)__float2ll_rn(sum * 1048576.0f));
+            atomicAdd(st + 1, (unsigned long long)__float2ll_rn(sq * 65536.0f));
+            node_epi_sync();
+            const float tsum = (float)(long long)st[0] * (1.0f / 1048576.0f), tsq = (float)(long long)st[1] * (1.0f / 65536.0f);
+            mean = tsum * (1.0f / 128.0f);
+            rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
+            node_epi_sync();
+            if (cq == 0) { st[0] = 0ull; st[1] = 0ull; }
         };
 
         if (p.do_update) {
-            // ---- E0: S row -> fp16 A operand; h_V row -> v ----
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            // ---- E0: S -> fp16 A operand; h_V -> v ----
+            {
                 float s32[32];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (live) { ldg_f32x8(p.S + (size_t)n * 128 + c * 32 + u * 8, s32 + u * 8); ldg_f32x8(p.hV + (size_t)n * 128 + c * 32 + u * 8, v + c * 32 + u * 8); }
+                    if (live) { ldg_f32x8(p.S + (size_t)n * 128 + c0 + u * 8, s32 + u * 8); ldg_f32x8(p.hV + (size_t)n * 128 + c0 + u * 8, v + u * 8); }
                     else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) { s32[u * 8 + e] = 0.f; v[c * 32 + u * 8 + e] = 0.f; }
+                        for (int e = 0; e < 8; ++e) { s32[u * 8 + e] = 0.f; v[u * 8 + e] = 0.f; }
                     }
                 }
-                store_row_chunk(hA, r, c * 32, s32);
+                store16(hA, 0, s32); store16(hA, 1, s32 + 16);
             }
             publish();
             // ---- EA: h1 = gate1 * (LN(h_V + (acc + cnt b3)/30) (1 + scale1) + shift1) ----
             wait_mma();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float acc[32], bb[32];
-                ld32(p.b3 + c * 32, bb);
-                tmem_ld32(tmem_row + c * 32, acc);
+            for (int g16 = 0; g16 < 2; ++g16) {
+                float acc[16], bb[16];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[c * 32 + e] += (acc[e] + cnt * bb[e]) * (1.0f / 30.0f);
+                for (int q = 0; q < 4; ++q) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.b3 + c0 + g16 * 16) + q); bb[q * 4] = t.x; bb[q * 4 + 1] = t.y; bb[q * 4 + 2] = t.z; bb[q * 4 + 3] = t.w; }
+                tmem_ld16(tmem_lane + (uint32_t)(g16 * 16), acc);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[g16 * 16 + e] += (acc[e] + cnt * bb[e]) * (1.0f / 30.0f);
             }
             {
                 float mean, rstd;
-                ln_stats(mean, rstd);
+                row_stats(mean, rstd);
+                float sh[32], sc[32], gt[32];
+                ld32(m, sh); ld32(m + 128, sc); ld32(m + 256, gt);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float sh[32], sc[32], gt[32];
-                    ld32(m + c * 32, sh); ld32(m + 128 + c * 32, sc); ld32(m + 256 + c * 32, gt);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int col = c * 32 + e;
-                        v[col] = gt[e] * fmaf((v[col] - mean) * rstd, 1.0f + sc[e], sh[e]);
-                    }
-                    store_row_chunk(hA, r, c * 32, v + c * 32);
-                }
+                for (int c = 0; c < 32; ++c) v[c] = gt[c] * fmaf((v[c] - mean) * rstd, 1.0f + sc[c], sh[c]);
+                store16(hA, 0, v); store16(hA, 1, v + 16);
             }
             publish();
             // ---- EG x2: FFN hidden = GELU(h1 Win^T + b_in), 256 columns per phase ----
@@ -242,15 +256,18 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
 #pragma unroll
                 for (int blk = 0; blk < 2; ++blk) {
                     unsigned char* dst = blk ? mid1 : mid0;
-                    const float* bi = p.bin + half * 256 + blk * 128;
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        float acc[32], bb[32];
-                        ld32(bi + c * 32, bb);
-                        tmem_ld32(tmem_row + (1 + blk) * 128 + c * 32, acc);
+                    const float* bi = p.bin + half * 256 + blk * 128 + c0;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) acc[e] = gelu_fast(acc[e] + bb[e]);
-                        store_row_chunk(dst, r, c * 32, acc);
+                    for (int g16 = 0; g16 < 2; ++g16) {
+                        float acc[16], bb[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { const float4 t = __ldg(reinterpret_cast<const float4*>(bi + g16 * 16) + q); bb[q * 4] = t.x; bb[q * 4 + 1] = t.y; bb[q * 4 + 2] = t.z; bb[q * 4 + 3] = t.w; }
+                        tmem_ld16(tmem_lane + (uint32_t)((1 + blk) * 128 + g16 * 16), acc);
+                        uint32_t o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = as_u32(gelu_h2(as_h2(pack_sat(acc[e * 2] + bb[e * 2], acc[e * 2 + 1] + bb[e * 2 + 1]))));
+                        *reinterpret_cast<uint4*>(dst + tile_off(r, (c0 >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4*>(dst + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
                 }
                 publish();
@@ -258,158 +275,144 @@ __global__ void __launch_bounds__(160, 1) node_tc_kernel(const __grid_constant__
             // ---- EB: h2 = mask * gate2 * (LN(h1 + acc3 + b_out) (1 + scale2) + shift2) ----
             wait_mma();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float acc[32], bb[32];
-                ld32(p.bout + c * 32, bb);
-                tmem_ld32(tmem_row + 3 * 128 + c * 32, acc);
+            for (int g16 = 0; g16 < 2; ++g16) {
+                float acc[16], bb[16];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[c * 32 + e] += acc[e] + bb[e];
+                for (int q = 0; q < 4; ++q) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bout + c0 + g16 * 16) + q); bb[q * 4] = t.x; bb[q * 4 + 1] = t.y; bb[q * 4 + 2] = t.z; bb[q * 4 + 3] = t.w; }
+                tmem_ld16(tmem_lane + (uint32_t)(3 * 128 + g16 * 16), acc);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[g16 * 16 + e] += acc[e] + bb[e];
             }
             {
                 float mean, rstd;
-                ln_stats(mean, rstd);
+                row_stats(mean, rstd);
+                float sh[32], sc[32], gt[32];
+                ld32(m + 384, sh); ld32(m + 512, sc); ld32(m + 640, gt);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float sh[32], sc[32], gt[32];
-                    ld32(m + 384 + c * 32, sh); ld32(m + 512 + c * 32, sc); ld32(m + 640 + c * 32, gt);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int col = c * 32 + e;
-                        v[col] = mk * (gt[e] * fmaf((v[col] - mean) * rstd, 1.0f + sc[e], sh[e]));
-                    }
-                }
+                for (int c = 0; c < 32; ++c) v[c] = mk * (gt[c] * fmaf((v[c] - mean) * rstd, 1.0f + sc[c], sh[c]));
             }
         } else {
             // ---- node init: h = x_in(x) ----
             float x0 = 0.f, x1 = 0.f, x2 = 0.f;
             if (live) { x0 = p.x[(size_t)n * 3]; x1 = p.x[(size_t)n * 3 + 1]; x2 = p.x[(size_t)n * 3 + 2]; }
+            float w0[32], w1[32], w2[32], bb[32];
+            ld32(p.xin_w_t + c0, w0); ld32(p.xin_w_t + 128 + c0, w1); ld32(p.xin_w_t + 256 + c0, w2); ld32(p.xin_b + c0, bb);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float w0[32], w1[32], w2[32], bb[32];
-                ld32(p.xin_w_t + c * 32, w0); ld32(p.xin_w_t + 128 + c * 32, w1); ld32(p.xin_w_t + 256 + c * 32, w2); ld32(p.xin_b + c * 32, bb);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[c * 32 + e] = live ? fmaf(x2, w2[e], fmaf(x1, w1[e], fmaf(x0, w0[e], bb[e]))) : 0.f;
-            }
+            for (int e = 0; e < 32; ++e) v[e] = live ? fmaf(x2, w2[e], fmaf(x1, w1[e], fmaf(x0, w0[e], bb[e]))) : 0.f;
         }
         // ---- write h_V (and the decoder's frozen encoder state), stage the projection operands ----
         const int enc_mode = p.n_proj > 0 ? p.proj[p.n_proj - 1].add_enc : 0;     // only the decoder-facing projection uses h'
+        if (live) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (live) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    stg_f32x8(p.hV + (size_t)n * 128 + c * 32 + u * 8, v + c * 32 + u * 8);
-                    if (p.write_enc) stg_f32x8(p.hVenc + (size_t)n * 128 + c * 32 + u * 8, v + c * 32 + u * 8);
-                }
-            }
-            if (p.n_proj > 0) {
-                store_row_chunk(hA, r, c * 32, v + c * 32);
-                if (enc_mode) {
-                    float hp[32];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float e8[8];
-                        if (enc_mode == 1 && live) ldg_f32x8(p.hVenc + (size_t)n * 128 + c * 32 + u * 8, e8);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float hv = v[c * 32 + u * 8 + e];
-                            hp[u * 8 + e] = enc_mode == 1 ? (live ? hv + e8[e] : 0.f) : 2.0f * hv;
-                        }
-                    }
-                    store_row_chunk(mid0, r, c * 32, hp);
-                }
+            for (int u = 0; u < 4; ++u) {
+                stg_f32x8(p.hV + (size_t)n * 128 + c0 + u * 8, v + u * 8);
+                if (p.write_enc) stg_f32x8(p.hVenc + (size_t)n * 128 + c0 + u * 8, v + u * 8);
             }
         }
         if (p.n_proj > 0) {
+            store16(hA, 0, v); store16(hA, 1, v + 16);
+            if (enc_mode) {
+                float hp[32];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float e8[8];
+                    if (enc_mode == 1 && live) ldg_f32x8(p.hVenc + (size_t)n * 128 + c0 + u * 8, e8);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float hv = v[u * 8 + e];
+                        hp[u * 8 + e] = enc_mode == 1 ? (live ? hv + e8[e] : 0.f) : 2.0f * hv;
+                    }
+                }
+                store16(mid0, 0, hp); store16(mid0, 1, hp + 16);
+            }
             publish();
-            // ---- EP: own halves (fp32, + bias) and gathered halves (fp16, + residue-type table) ----
+            // ---- EP: own halves (+ bias) and gathered halves (+ residue-type table) -> P16 (fp16) ----
             wait_mma();
             for (int j = 0; j < p.n_proj; ++j) {
                 const ProjTc pj = p.proj[j];
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    float acc[32], bb[32];
-                    ld32(pj.ba + c * 32, bb);
-                    tmem_ld32(tmem_row + (2 * j) * 128 + c * 32, acc);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) acc[e] += bb[e];
+                for (int which = 0; which < 2; ++which) {
+                    float acc[32], add[32];
+                    if (which == 0) ld32(pj.ba + c0, add);
+                    else if (pj.table != nullptr) ld32(pj.table + zres * 128 + c0, add);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) add[e] = 0.f;
+                    }
+                    tmem_ld32(tmem_lane + (uint32_t)((2 * j + which) * 128), acc);
                     if (live) {
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             uint32_t o[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) o[e] = f2_to_h2(acc[u * 16 + e * 2], acc[u * 16 + e * 2 + 1]);
-                            stg256(pj.out16 + (size_t)n * 256 + c * 32 + u * 16, o);
-                        }
-                    }
-                    tmem_ld32(tmem_row + (2 * j + 1) * 128 + c * 32, acc);
-                    if (pj.table != nullptr) {
-                        const float4* tb = reinterpret_cast<const float4*>(pj.table + zres * 128 + c * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = __ldg(tb + q);
-                            acc[q * 4] += t.x; acc[q * 4 + 1] += t.y; acc[q * 4 + 2] += t.z; acc[q * 4 + 3] += t.w;
-                        }
-                    }
-                    if (live) {
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            uint32_t o[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) o[e] = f2_to_h2(acc[u * 16 + e * 2], acc[u * 16 + e * 2 + 1]);
-                            stg256(pj.out16 + (size_t)n * 256 + 128 + c * 32 + u * 16, o);
+                            for (int e = 0; e < 8; ++e) o[e] = f2_to_h2(acc[u * 16 + e * 2] + add[u * 16 + e * 2], acc[u * 16 + e * 2 + 1] + add[u * 16 + e * 2 + 1]);
+                            stg256(pj.out16 + (size_t)n * 256 + which * 128 + c0 + u * 16, o);
                         }
                     }
                 }
             }
         }
-        if (p.do_final && live) {
-            // ---- FinalLayer (adaLN modulate + Linear 128 -> 6) fused with the DDPM p_sample update ----
-            float mean, rstd;
-            ln_stats(mean, rstd);
-            const float* fm = p.fin_mod + (size_t)b * p.mod_stride;      // [shift | scale]
-            float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (p.do_final) {
+            // ---- FinalLayer (adaLN modulate + Linear 128 -> 6) fused with the DDPM p_sample update: one thread per row
+            //      re-reads the full row it and its three column-quarter partners just wrote ----
+            node_epi_sync();
+            if (cq == 0 && live) {
+                const float* hrow = p.hV + (size_t)n * 128;
+                float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+                for (int u = 0; u < 16; ++u) {
+                    float h8[8];
+                    ldg_f32x8(hrow + u * 8, h8);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float sh[32], sc[32];
-                ld32(fm + c * 32, sh); ld32(fm + 128 + c * 32, sc);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float t = fmaf((v[c * 32 + e] - mean) * rstd, 1.0f + sc[e], sh[e]);
-                    const float2* w = reinterpret_cast<const float2*>(p.fin_w_t + (c * 32 + e) * 6);
-                    const float2 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-                    o[0] = fmaf(t, w0.x, o[0]); o[1] = fmaf(t, w0.y, o[1]); o[2] = fmaf(t, w1.x, o[2]);
-                    o[3] = fmaf(t, w1.y, o[3]); o[4] = fmaf(t, w2.x, o[4]); o[5] = fmaf(t, w2.y, o[5]);
+                    for (int e = 0; e < 8; ++e) { sum += h8[e]; sq = fmaf(h8[e], h8[e], sq); }
                 }
-            }
+                const float mean = sum * (1.0f / 128.0f);
+                const float rstd = rsqrtf(fmaxf(sq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
+                const float* fm = p.fin_mod + (size_t)b * p.mod_stride;      // [shift | scale]
+                float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int u = 0; u < 16; ++u) {
+                    float h8[8];
+                    ldg_f32x8(hrow + u * 8, h8);
 #pragma unroll
-            for (int u = 0; u < 6; ++u) { o[u] += __ldg(p.fin_b + u); p.out6[(size_t)n * 6 + u] = o[u]; }
-            if (p.x_next != nullptr) {
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = u * 8 + e;
+                        const float t = fmaf((h8[e] - mean) * rstd, 1.0f + __ldg(fm + 128 + c), __ldg(fm + c));
+                        const float2* w = reinterpret_cast<const float2*>(p.fin_w_t + c * 6);
+                        const float2 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                        o[0] = fmaf(t, w0.x, o[0]); o[1] = fmaf(t, w0.y, o[1]); o[2] = fmaf(t, w1.x, o[2]);
+                        o[3] = fmaf(t, w1.y, o[3]); o[4] = fmaf(t, w2.x, o[4]); o[5] = fmaf(t, w2.y, o[5]);
+                    }
+                }
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const float eps = o[d], vv = o[3 + d];
-                    const float x = p.x_t[(size_t)n * 3 + d];
-                    const float frac = (vv + 1.0f) / 2.0f;
-                    const float logvar = frac * p.coef[1] + (1.0f - frac) * p.coef[0];
-                    const float x0 = p.coef[2] * x - p.coef[3] * eps;
-                    const float mean_ = p.coef[4] * x0 + p.coef[5] * x;
-                    p.x_next[(size_t)n * 3 + d] = mean_ + p.coef[6] * expf(0.5f * logvar) * p.noise[(size_t)n * 3 + d];
+                for (int u = 0; u < 6; ++u) { o[u] += __ldg(p.fin_b + u); p.out6[(size_t)n * 6 + u] = o[u]; }
+                if (p.x_next != nullptr) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float eps = o[d], vv = o[3 + d];
+                        const float x = p.x_t[(size_t)n * 3 + d];
+                        const float frac = (vv + 1.0f) / 2.0f;
+                        const float logvar = frac * p.coef[1] + (1.0f - frac) * p.coef[0];
+                        const float x0 = p.coef[2] * x - p.coef[3] * eps;
+                        const float mean_ = p.coef[4] * x0 + p.coef[5] * x;
+                        p.x_next[(size_t)n * 3 + d] = mean_ + p.coef[6] * expf(0.5f * logvar) * p.noise[(size_t)n * 3 + d];
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-constexpr size_t NODE_TC_SMEM = 7 * (size_t)TILE_BYTES + 64 + 1024;
+constexpr size_t NODE_TC_SMEM = 7 * (size_t)TILE_BYTES + 2048 + 64;
 
 struct NodeTcState { CUtensorMap wmap; };
 
 int node_tc_launch(Plan& p, NodeTcParams& np, cudaStream_t s) {
     const NodeTcState& st = *reinterpret_cast<const NodeTcState*>(p.node_tc);
-    node_tc_kernel<<<(np.N + 127) / 128, 160, NODE_TC_SMEM, s>>>(st.wmap, np);
+    node_tc_kernel<<<(np.N + 127) / 128, NODE_EPI_THREADS + 32, NODE_TC_SMEM, s>>>(st.wmap, np);
     CB2_LAUNCH_CHECK();
     p.launches++;
     return 0;

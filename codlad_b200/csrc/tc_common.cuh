@@ -133,6 +133,26 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
                  ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+// packed-half helpers of the epilogues
+__device__ __forceinline__ uint32_t pack_sat(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// erf-GELU ~= 0.5 x (1 + tanh(x (a + b x^2))) on two fp16 values (coefficients refitted, see gelu_fast)
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+    const __half2 x2 = __hmul2(x, x);
+    const __half2 pl = __hfma2(x2, __float2half2_rn(0.03470094f), __float2half2_rn(0.80015698f));
+    const __half2 u = __hmul2(x, pl);
+    uint32_t t;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(as_u32(u)));
+    const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
+    return __hfma2(h, as_h2(t), h);
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
