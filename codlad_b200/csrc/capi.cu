@@ -395,13 +395,24 @@ void cb2_vae_destroy(cb2_vae* h) {
 
 // ------------------------------------------------------------------------------------------- plan
 int cb2_plan_create(const cb2_denoiser* d, int F, int NB, int L, int precision, int keep_debug, cb2_plan** out) {
-    if (!d || !out || F <= 0 || NB <= 0 || L <= 0) { set_error("plan_create: bad argument"); return 1; }
+    if (!out || F <= 0 || NB <= 0 || L <= 0) { set_error("plan_create: bad argument"); return 1; }
     if (precision != PREC_F32 && precision != PREC_F16) { set_error("plan_create: unknown precision %d", precision); return 1; }
     cb2_plan* h = new cb2_plan();
     Plan& p = h->p;
-    p.model = &d->m; p.F = F; p.NB = NB; p.L = L; p.precision = precision;
-    p.K = d->m.k_neighbors < L ? d->m.k_neighbors : L;
+    p.model = d ? &d->m : nullptr; p.F = F; p.NB = NB; p.L = L; p.precision = precision;
     h->keep_debug = keep_debug;
+    if (!d) {
+        // decode-only plan (no denoiser): just the frame geometry the VQ / IC decoder / ic_to_xyz side needs
+        int e = 0;
+        e |= dev_alloc(p.allocs, &p.X, (size_t)F * L * 3);
+        e |= dev_alloc(p.allocs, &p.lengths, F);
+        e |= dev_alloc(p.allocs, &p.cg_z, (size_t)F * L);
+        e |= dev_alloc(p.allocs, &p.frame_of, NB);
+        if (e) { cb2_plan_destroy(h); return e; }
+        *out = h;
+        return 0;
+    }
+    p.K = d->m.k_neighbors < L ? d->m.k_neighbors : L;
     const size_t N = (size_t)NB * L, FE = (size_t)F * L * p.K, NE = N * p.K;
     const size_t esz = precision == PREC_F16 ? 2 : 4;
     int e = 0;
@@ -460,6 +471,7 @@ int cb2_plan_set_frames(cb2_plan* h, const float* X, const int* lengths, const i
     CB2_CUDA(cudaMemcpyAsync(p.lengths, lengths, p.F * sizeof(int), cudaMemcpyDeviceToDevice, s));
     CB2_CUDA(cudaMemcpyAsync(p.cg_z, cg_z, (size_t)p.F * p.L * sizeof(int), cudaMemcpyDeviceToDevice, s));
     CB2_CUDA(cudaMemcpyAsync(p.frame_of, frame_of, p.NB * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    if (p.model == nullptr) { h->frames_ready = true; return 0; }      // decode-only plan
     if (int e = launch_knn(p.X, p.lengths, p.F, p.L, p.K, p.nbr_dist, p.nbr_idx, s)) return e;
     if (int e = launch_edge_features(*p.model, p.X, p.lengths, p.nbr_idx, p.nbr_dist, p.F, p.L, p.K, p.E_dbg, p.hE0, p.precision, s)) return e;
     p.launches += 2;
@@ -512,7 +524,7 @@ extern "C" {
 
 int cb2_plan_forward_partial(cb2_plan* h, const float* x, const float* t, int stop_after, void* stream) {
     if (!h || !x || !t) { set_error("forward_partial: null argument"); return 1; }
-    if (!h->frames_ready) { set_error("forward_partial: cb2_plan_set_frames has not been called"); return 1; }
+    if (!h->frames_ready || !h->p.model) { set_error("forward_partial: no denoiser frames on this plan"); return 1; }
     Plan& p = h->p;
     cudaStream_t s = (cudaStream_t)stream;
     if (int e = launch_timestep_mod(*p.model, t, p.NB, p.silu_c, p.mod, p.mod16, s)) return e;
@@ -522,7 +534,7 @@ int cb2_plan_forward_partial(cb2_plan* h, const float* x, const float* t, int st
 
 int cb2_plan_forward(cb2_plan* h, const float* x, const float* t, float* out, void* stream) {
     if (!h || !x || !t || !out) { set_error("forward: null argument"); return 1; }
-    if (!h->frames_ready) { set_error("forward: cb2_plan_set_frames has not been called"); return 1; }
+    if (!h->frames_ready || !h->p.model) { set_error("forward: cb2_plan_set_frames has not been called (or decode-only plan)"); return 1; }
     Plan& p = h->p;
     cudaStream_t s = (cudaStream_t)stream;
     if (p.NB > p.mod_capacity) { set_error("forward: NB exceeds table capacity"); return 1; }
@@ -535,7 +547,7 @@ int cb2_plan_forward(cb2_plan* h, const float* x, const float* t, float* out, vo
 }
 
 int cb2_plan_set_schedule(cb2_plan* h, const float* t_of_step, const float* coef, int T, void* stream) {
-    if (!h || !t_of_step || !coef || T <= 0) { set_error("set_schedule: bad argument"); return 1; }
+    if (!h || !t_of_step || !coef || T <= 0 || !h->p.model) { set_error("set_schedule: bad argument"); return 1; }
     Plan& p = h->p;
     cudaStream_t s = (cudaStream_t)stream;
     if (T > p.mod_capacity) { set_error("set_schedule: T=%d exceeds capacity %d", T, p.mod_capacity); return 1; }

@@ -76,8 +76,9 @@ class Plan:
         self.denoiser = denoiser
         self.F, self.NB, self.L, self.precision = int(F), int(NB), int(L), precision
         h = C.c_void_p()
-        N.check(N.lib().cb2_plan_create(denoiser.handle, self.F, self.NB, self.L, N.PRECISION[precision], int(keep_debug), C.byref(h)),
-                "plan_create")
+        N.require_cuda()
+        N.check(N.lib().cb2_plan_create(denoiser.handle if denoiser is not None else None, self.F, self.NB, self.L,
+                                        N.PRECISION[precision], int(keep_debug), C.byref(h)), "plan_create")
         self.handle = h
         self.K = N.lib().cb2_plan_K(h)
         self.device = torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,31 @@
+"""Internal coordinates -> Cartesian behind the reference's signature (reference utils/utils_ic.py:242-268)."""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+from . import topology
+
+
+def ic_to_xyz(CG_nxyz, ic_recon, info):
+    """CG_nxyz [B, L+2, 4] (column 0 = residue type; the untrimmed C-alpha trace), ic_recon [B, L, 13, 3]
+    (bond, angle, torsion), info = (permute, atom_idx, atom_orders [10, L, 3]) -> [B, Na, 3] on the CUDA device.
+    One thread per (frame, residue) places the 13 atoms in registers (csrc/decode.cu)."""
+    N.require_cuda()
+    B, Lp2, _ = CG_nxyz.shape
+    L = Lp2 - 2
+    dev = torch.device("cuda", torch.cuda.current_device())
+    permute, atom_idx, atom_orders = info
+    na = int(permute.numel())
+    ca = CG_nxyz[..., 1:].to(dev, torch.float32).contiguous()
+    ic = ic_recon.to(dev, torch.float32).reshape(B, L, 13, 3).contiguous()
+    # one topology shared by the B frames: replicate the (small) per-frame tables so one launch covers the batch
+    orders = atom_orders.permute(1, 0, 2).to(torch.int8).contiguous().to(dev)[None].expand(B, -1, -1, -1).contiguous()
+    slot = topology.slot_to_atom_map(info, L).to(dev)[None].expand(B, -1).contiguous()
+    frame_of = torch.arange(B, dtype=torch.int32, device=dev)
+    lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+    out_off = (torch.arange(B, dtype=torch.int64) * na).to(dev)
+    xyz = torch.zeros(B * na, 3, device=dev)
+    N.check(N.lib().cb2_ic_to_xyz(N.dptr(ca), N.dptr(ic), B, L, N.dptr(frame_of), N.dptr(lengths), N.dptr(orders), N.dptr(slot),
+                                  N.dptr(out_off), N.dptr(xyz), N.stream_ptr()), "ic_to_xyz")
+    return xyz.reshape(B, na, 3)

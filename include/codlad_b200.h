@@ -60,7 +60,8 @@ CB2_API void cb2_vae_destroy(cb2_vae* v);
 
 /* ---- plan: one batch geometry ------------------------------------------------------------------
  * F frames (distinct C-alpha traces) padded to L residues, NB batch members; member b denoises over
- * frame frame_of[b] (an ensemble = several members on one frame).  K = min(k_neighbors, L). */
+ * frame frame_of[b] (an ensemble = several members on one frame).  K = min(k_neighbors, L).
+ * m may be NULL: a decode-only plan (set_frames / set_topology / decode work; forward / sample refuse). */
 CB2_API int cb2_plan_create(const cb2_denoiser* m, int F, int NB, int L, int precision, int keep_debug, cb2_plan** out);
 CB2_API void cb2_plan_destroy(cb2_plan* p);
 CB2_API int cb2_plan_K(const cb2_plan* p);

@@ -388,3 +388,66 @@ def test_full_path_config1_fp32(eng, R):
     assert torch.equal(out["idx"].cpu().long(), idx_ref)
     xyz_ref = R.ic_to_xyz(batch["OG_CG_nxyz"].reshape(-1, 66, 4), ic_ref.reshape(1, 64, 13, 3), prot.info)
     assert P.rmsd(out["xyz"].cpu().reshape(1, -1, 3), xyz_ref) < 1e-3
+
+
+# --------------------------------------------------------------------------------------- reference call surface (drop-in)
+def test_reference_call_surface_end_to_end(R):
+    """The path exactly as test.py drives it (test.py:495-582): model factory + load_state_dict, create_diffusion,
+    doubled batch cat([z, z]), p_sample_loop(model.forward, ...), chunk(2)[0], get_norm_feature(norm_in=False),
+    latent_decode, ic_to_xyz -- each stage against the CPU oracle."""
+    from codlad_b200.diffusion import create_diffusion
+    from codlad_b200.latent_model import MPNN_models
+    from codlad_b200.utils_ic import ic_to_xyz
+    from codlad_b200.vae_model import VAE, get_norm_feature
+    dsd, vsd = weights.init_denoiser_state(3), weights.init_vae_decode_state(3)
+    model = MPNN_models["mpnn_diffusion"](input_size=3, unconditional=True, diffusion="diffusion", precision="fp32")
+    assert list(model.state_dict().keys()) == list(dsd.keys())
+    model.load_state_dict({"module." + k: v for k, v in dsd.items()})          # DDP-prefixed checkpoint, test.py:277-285
+    vae = VAE("N6")
+    vae.load_state_dict(vsd)
+    T, L, Fr = 20, 56, 2
+    diffusion = create_diffusion(str(T))
+    prot = synthetic.make_protein(L, Fr, seed=4242)
+    batch = synthetic.collate(prot)
+    mask = torch.ones(Fr, L, dtype=torch.bool)
+    z = synthetic.latent_noise((Fr, L, 3), 7)
+    noises = synthetic.latent_noise((T, Fr, L, 3), 8)
+    cat_z, cat_mask = torch.cat([z, z], 0), torch.cat([mask, mask], 0)
+    samples = diffusion.p_sample_loop(model.forward, cat_z.shape, cat_z.cuda(), clip_denoised=False,
+                                      model_kwargs=dict(y=None, mask=cat_mask.cuda(), batch=batch), device="cuda",
+                                      step_noise=torch.cat([noises, noises], 1))
+    first, second = samples.chunk(2, dim=0)
+    assert torch.equal(first, second)                                          # both halves of the doubled batch are the same sample
+    X = prot.ca_full[:, 1:-1].contiguous()
+    zz = prot.restype_full[1:-1][None].expand(Fr, -1)
+    ref_lat = R.sample_loop(dsd, z, X, zz, mask, noises, R.respaced_schedule(T))
+    assert P.rel_err(first.cpu(), ref_lat) < 1e-4
+    lat = get_norm_feature(first, "latent", True, False, norm_in=False, dataname="PED_N6")
+    mean, std = (torch.tensor(v) for v in weights.LATENT_STATS[("N6", "PED")])
+    assert torch.equal(lat.cpu(), first.cpu() * std + mean)
+    zq, idx, loss = vae.quantize(lat, mask=mask.cuda())
+    _, ic_recon = vae.latent_decode(lat, mask.cuda(), batch)
+    ic_ref, idx_ref = R.latent_decode(vsd, lat.cpu(), mask, batch["CG_nxyz"][:, 0].long(), batch["CG_nxyz"][:, 1:], batch["CG_nbr_list"],
+                                      batch["num_CGs"], False)
+    assert torch.equal(idx.cpu(), idx_ref) and float(loss) == 0.0
+    assert ic_recon.shape == ic_ref.shape and P.rel_err(ic_recon.cpu(), ic_ref) < 1e-5
+    og = batch["OG_CG_nxyz"].reshape(-1, L + 2, 4)
+    xyz = ic_to_xyz(og, ic_recon.reshape(-1, L, 13, 3), prot.info)
+    xyz_ref = R.ic_to_xyz(og, ic_ref.reshape(-1, L, 13, 3), prot.info)
+    assert xyz.shape == xyz_ref.shape and P.rmsd(xyz.cpu(), xyz_ref) < 1e-3
+
+
+def test_module_forward_matches_oracle_ragged_batch(R):
+    """forward(x, t, y, mask, batch) on a ragged two-protein batch (padding + mask), fp32 tier."""
+    from codlad_b200.latent_model import MPNN_models
+    sd = weights.init_denoiser_state(0)
+    model = MPNN_models["mpnn_diffusion"](precision="fp32")
+    model.load_state_dict(sd)
+    g = P.golden("denoiser_ragged")
+    c = P.denoiser_case(g["meta"], [80, 70])
+    cg = torch.cat([torch.cat([c["cg_z"][b, :n, None].float(), c["X"][b, :n]], 1) for b, n in enumerate([80, 70])], 0)
+    batch = {"CG_nxyz": cg, "num_CGs": torch.tensor([80, 70])}
+    out = model(c["x"].cuda(), c["t"].cuda(), None, mask=c["mask"].cuda(), batch=batch).cpu()
+    m = c["mask"] & torch.tensor([True, True])[:, None]
+    m[1] = False                                       # rows of the shorter protein see topk's arbitrary tie order in the reference
+    assert np.abs(out.numpy() - g["out"])[m.numpy()].max() < 5e-5

@@ -79,3 +79,23 @@ def test_frames_from_batch_ragged():
     assert torch.equal(fs.X[1, :25], prots[1].ca_full[0, 1:-1]) and float(fs.X[1, 25:].abs().sum()) == 0
     assert int(fs.csr_row[40 + 25]) == int(fs.csr_row[-1])          # padded rows have no edges
     assert fs.out_off.tolist() == [0, prots[0].num_atoms]
+
+
+def test_reference_surface_modules_have_reference_state_dict_keys():
+    """Module construction is CPU-only; only forward needs the GPU.  Keys / shapes are the drop-in contract."""
+    from codlad_b200 import weights
+    from codlad_b200.latent_model import MPNN_models, fused_sampler_for
+    from codlad_b200.vae_model import VAE, get_norm_feature
+    m = MPNN_models["mpnn_diffusion"](input_size=3, unconditional=True, diffusion="diffusion", self_condition=False)
+    want = weights.denoiser_shapes()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(want.keys()) and len(sd) == 108
+    assert all(tuple(sd[k].shape) == tuple(v) for k, v in want.items())
+    assert sum(v.numel() for v in sd.values()) == 2449974                   # SURVEY.md section 5: parameter count of the reference
+    assert fused_sampler_for(m.forward) is not None and fused_sampler_for(lambda *a: None) is None
+    for vt, angle in (("N6", False), ("K4", True)):
+        v = VAE(vt)
+        assert list(v.state_dict().keys()) == list(weights.vae_decode_shapes(angle).keys())
+    import torch
+    x = torch.randn(2, 5, 3)
+    assert torch.allclose(get_norm_feature(get_norm_feature(x, norm_in=False, dataname="Atlas_K4"), norm_in=True, dataname="Atlas_K4"), x, atol=1e-5)
