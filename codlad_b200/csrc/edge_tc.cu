@@ -66,27 +66,28 @@ constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 K
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the epilogue threads only
 
 // per-thread view of a tile, packed into two registers (four of them are live; they rotate so that the stage code
-// exists once):  a = node0 | q_of_row << 26 | nv << 28 ;  b = neighbour node | keep << 31
+// exists once):  a = node0 | q_of_row << 26 | nv << 28 ;  b = member-local neighbour index j (raw: nothing waits on its load
+// until the next round's E1), or 0x80000000 for a row outside the tile
 struct TileMeta { uint32_t a, b; };
 __device__ __forceinline__ int meta_node0(const TileMeta& m) { return (int)(m.a & 0x3ffffffu); }
 __device__ __forceinline__ int meta_q(const TileMeta& m) { return (int)((m.a >> 26) & 3u); }
 __device__ __forceinline__ int meta_nv(const TileMeta& m) { return (int)(m.a >> 28); }
-__device__ __forceinline__ int meta_pc_node(const TileMeta& m) { return (int)(m.b & 0x7fffffffu); }
-__device__ __forceinline__ uint32_t meta_keep(const TileMeta& m) { return (uint32_t)((int)m.b >> 31); }
+__device__ __forceinline__ int meta_j(const TileMeta& m) { return (int)(m.b & 0x7fffffffu); }
+__device__ __forceinline__ bool meta_row_valid(const TileMeta& m) { return (int)m.b >= 0; }
 
 template <int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int N_W = MODE == EDGE_ENC_EDGE ? 3 : 2;
-    // layout: [weights N_W x 32 KB][4 tile slots x 32 KB][indicator 4 KB | LN statistics 1 KB][barriers]
+    // layout: [weights N_W x 32 KB][4 tile slots x 32 KB][indicator 4 KB (ENC_NODE / DEC)][barriers]
     unsigned char* sW = smem;
     unsigned char* sT = sW + N_W * TILE_BYTES;
     unsigned char* sAux = sT + 4 * TILE_BYTES;
     unsigned char* sInd = sAux;                                                   // ENC_NODE / DEC
-    unsigned long long* sStat = reinterpret_cast<unsigned long long*>(sAux);      // ENC_EDGE: [128 rows][sum, sum of squares], fixed point
-    // barriers: [0] weights; per tile slot g: [1+3g] load (TMA tx), [2+3g] acc (MMA commit), [3+3g] epi (512 arrivals); [13+g] go
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sAux + (MODE == EDGE_ENC_EDGE ? 2048 : IND_BYTES));
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 17);
+    // barriers: [0] weights; per tile slot g: [1+3g] load (TMA tx), [2+3g] acc (MMA commit), [3+3g] epi (16 warp arrivals); [13+g] go;
+    // ENC_EDGE: [17+g] MMA 3 complete (operand tile reusable), [21+g] residual re-load landed
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sAux + (MODE == EDGE_ENC_EDGE ? 0 : IND_BYTES));
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 25);
 
     const int tid = threadIdx.x;
     const int K = p.K, NPT = p.NPT;
@@ -98,8 +99,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         for (int g = 0; g < 4; ++g) {
             mbar_init(smem_u32(&sBar[1 + 3 * g]), 1);
             mbar_init(smem_u32(&sBar[2 + 3 * g]), 1);
-            mbar_init(smem_u32(&sBar[3 + 3 * g]), EPI_THREADS);
+            mbar_init(smem_u32(&sBar[3 + 3 * g]), EPI_THREADS / 32);          // one arrival per epilogue warp
             mbar_init(smem_u32(&sBar[13 + g]), 1);
+            mbar_init(smem_u32(&sBar[17 + g]), 1);
+            mbar_init(smem_u32(&sBar[21 + g]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -122,8 +125,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             const uint32_t off = (uint32_t)((c16 >> 3) * (16 * 128) + q * 128 + (((c16 & 7) ^ (q & 7)) << 4));
             *reinterpret_cast<uint4*>(sInd + off) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-    } else if (tid < 256) {
-        sStat[tid] = 0ull;
     }
     fence_async_smem();
     tc_fence_before();
@@ -144,6 +145,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         auto bar_acc = [&](int g) { return smem_u32(&sBar[2 + 3 * g]); };
         auto bar_epi = [&](int g) { return smem_u32(&sBar[3 + 3 * g]); };
         auto bar_go = [&](int g) { return smem_u32(&sBar[13 + g]); };          // slot g's operand tile may be recycled
+        auto bar_m3 = [&](int g) { return smem_u32(&sBar[17 + g]); };          // ENC_EDGE: MMA 3 complete
+        auto bar_res = [&](int g) { return smem_u32(&sBar[21 + g]); };         // ENC_EDGE: residual rows re-loaded into the tile
         if (tid == EPI_THREADS + 32) {
             // ------------------------------------------------------------------ TMA thread
             const CUtensorMap* in_map = p.in_is_frame ? &maps.in_frame : &maps.state;
@@ -151,22 +154,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             for (int m = 0; m < N_W; ++m)
                 for (int h = 0; h < 2; ++h)
                     tma_load_2d(smem_u32(sW + m * TILE_BYTES + h * HALF_BYTES), &maps.weights, h * 64, p.w_row[m], smem_u32(&sBar[0]));
-            int nv[4], out_row0[4];
-            auto issue_load = [&](int g, int t) {                     // TMA of the tile's h_E rows, one box per node and half
+            int nv[4], out_row0[4], in_row0[4];
+            auto issue_rows = [&](int g, uint32_t bar) {              // TMA of the tile's h_E rows, one box per node and half
+                mbar_expect_tx(bar, (uint32_t)(nv[g] * K * 256));
+                for (int q = 0; q < nv[g]; ++q)
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d(T_u32(g) + h * HALF_BYTES + q * K * 128, in_map, h * 64, in_row0[g] + q * K, bar);
+            };
+            auto issue_load = [&](int g, int t) {
                 const int b = t / p.tiles_per_member;
                 const int i0 = (t - b * p.tiles_per_member) * NPT;
                 nv[g] = min(NPT, p.L - i0);
-                const int in_row0 = ((p.in_is_frame ? __ldg(p.frame_of + b) : b) * p.L + i0) * K;
+                in_row0[g] = ((p.in_is_frame ? __ldg(p.frame_of + b) : b) * p.L + i0) * K;
                 out_row0[g] = (b * p.L + i0) * K;
-                mbar_expect_tx(bar_load(g), (uint32_t)(nv[g] * K * 256));
-                for (int q = 0; q < nv[g]; ++q)
-                    for (int h = 0; h < 2; ++h)
-                        tma_load_2d(T_u32(g) + h * HALF_BYTES + q * K * 128, in_map, h * 64, in_row0 + q * K, bar_load(g));
+                issue_rows(g, bar_load(g));
             };
             for (int g = 0; g < 4; ++g)
                 if (blockIdx.x * 4 + g < p.n_tiles) issue_load(g, blockIdx.x * 4 + g);
             uint32_t ph_go = 0;
             for (int t0 = blockIdx.x * 4; t0 < p.n_tiles; t0 += tile_stride) {
+                if (MODE == EDGE_ENC_EDGE) {
+                    // residual of the edge update: once MMA 3 has consumed the activation tile, the tile's original h_E rows are
+                    // loaded into it again, so E3 reads its residual from shared memory instead of waiting on L2
+                    for (int g = 0; g < 4 && t0 + g < p.n_tiles; ++g) { mbar_wait(bar_m3(g), ph_go); issue_rows(g, bar_res(g)); }
+                }
                 for (int g = 0; g < 4; ++g) {
                     const int t = t0 + g;
                     if (t >= p.n_tiles) break;
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 ph_epi ^= 1;
                 for (int g = 0; g < n; ++g) {                                                                  // E2 done -> reduction MMA / MMA 3
                     mbar_wait(bar_epi(g), ph_epi);
-                    if (MODE == EDGE_ENC_EDGE) issue_mma(g, 2); else issue_reduce(g);
+                    if (MODE == EDGE_ENC_EDGE) { issue_mma(g, 2); umma_commit(bar_m3(g)); } else issue_reduce(g);
                 }
                 ph_epi ^= 1;
                 // E3 done: the accumulator is drained -> MMA 1 of the slot's next tile as soon as its TMA has landed.
@@ -243,6 +254,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         const int q_of_r = r / K;
         const int len0 = __ldg(p.lengths);                             // length of frame 0 (the only frame of an ensemble plan)
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        // stage hand-off to the control lanes: every thread orders its own smem writes / TMEM reads, the warp converges,
+        // one lane arrives (512 arrivals on one mbarrier word would serialise)
+        auto stage_done = [&](int s, bool wrote_smem) {
+            if (wrote_smem) fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(smem_u32(&sBar[3 + 3 * s]));
+        };
 
         // metadata of tile `tile` for this thread (global loads; consumed a full round later)
         auto load_meta = [&](int tile) {
@@ -251,25 +270,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             const int b = tile / p.tiles_per_member;
             const int i0 = (tile - b * p.tiles_per_member) * NPT;
             const int nv = min(NPT, p.L - i0);
-            const int f = p.single_frame ? 0 : __ldg(p.frame_of + b);    // (dependent loads only for multi-frame plans)
-            const int len = p.single_frame ? len0 : __ldg(p.lengths + f);
-            int j = 0, qq = 0;
-            uint32_t keep = 0u;
+            const int f = p.single_frame ? 0 : __ldg(p.frame_of + b);    // (dependent load only for multi-frame plans)
+            int qq = 0;
+            m.b = 0x80000000u;
             if (q_of_r < nv) {
-                const int i = i0 + q_of_r;
                 qq = q_of_r;
-                j = __ldg(p.nbr_idx + ((size_t)f * p.L + i) * K + (r - q_of_r * K));
-                keep = (MODE == EDGE_DEC || (i < len && j < len)) ? 1u : 0u;
+                m.b = (uint32_t)__ldg(p.nbr_idx + ((size_t)f * p.L + i0 + q_of_r) * K + (r - q_of_r * K));
             }
             m.a = (uint32_t)(b * p.L + i0) | ((uint32_t)qq << 26) | ((uint32_t)nv << 28);
-            m.b = (uint32_t)(b * p.L + j) | (keep << 31);
             return m;
         };
         auto prefetch_pa = [&](const TileMeta& m) {                     // pull the own-half segment of the next stage into L1
             asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P16 + (size_t)(meta_node0(m) + meta_q(m)) * 256 + c0));
         };
+        // neighbour-sum mask of this thread's row (reference: mask_attend = mask_i mask_j; the decoder passes no mask)
+        auto row_keep = [&](const TileMeta& m) -> uint32_t {
+            if (!meta_row_valid(m)) return 0u;
+            if (MODE == EDGE_DEC) return 0xffffffffu;
+            const int node0 = meta_node0(m), b = node0 / p.L;
+            const int len = p.single_frame ? len0 : __ldg(p.lengths + __ldg(p.frame_of + b));
+            return (node0 - b * p.L + meta_q(m) < len && meta_j(m) < len) ? 0xffffffffu : 0u;
+        };
         auto ld_pc = [&](const TileMeta& m, uint32_t (&pc)[16]) {       // this thread's 32 gathered halves of Pc[j]
-            const __half* src = p.P16 + (size_t)meta_pc_node(m) * 256 + 128 + c0;
+            const int b = meta_node0(m) / p.L;
+            const __half* src = p.P16 + ((size_t)b * p.L + meta_j(m)) * 256 + 128 + c0;
             ldg256(src, *reinterpret_cast<uint32_t(*)[8]>(&pc[0]));
             ldg256(src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[8]));
         };
@@ -279,10 +303,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         };
 
+        unsigned long long* trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
+        int n_trace = 0;
+        auto mark = [&](int ev, int s) {               // debug timeline (off unless the plan's "tc_trace" buffer was requested)
+            if (trace != nullptr && n_trace < 500) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                trace[1 + n_trace] = (t << 8) | (unsigned long long)((ev << 2) | s);
+                trace[0] = (unsigned long long)(++n_trace);
+            }
+        };
         TileMeta m0 = load_meta(blockIdx.x * NSLOT + 0), m1 = load_meta(blockIdx.x * NSLOT + 1),
                  m2 = load_meta(blockIdx.x * NSLOT + 2), m3 = load_meta(blockIdx.x * NSLOT + 3);
         auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
+        uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
         uint32_t pcA[16], pcB[16];                                      // gathered halves, double buffered one stage ahead
         ld_pc(m0, pcA);
 
@@ -295,8 +330,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 const __half* pa_src = p.P16 + (size_t)(meta_node0(m0) + meta_q(m0)) * 256 + c0;
                 ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
                 ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
+                mark(0, s);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                 tc_fence_after();
+                mark(1, s);
 #pragma unroll
                 for (int g16 = 0; g16 < 2; ++g16) {
                     float acc[16];
@@ -309,7 +346,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     }
                     st16(T, g16, o);
                 }
-                fence_async_smem(); tc_fence_before(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));
+                mark(2, s);
+                stage_done(s, true);
+                mark(3, s);
             };
 #pragma unroll 1
             for (int s2 = 0; s2 < NSLOT; s2 += 2) {
@@ -324,12 +363,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             for (int s = 0; s < NSLOT; ++s) {
                 if (s < n) {
                     unsigned char* T = sT + s * TILE_BYTES;
-                    const uint32_t keep = MODE == EDGE_ENC_EDGE ? 0xffffffffu : meta_keep(m0);
+                    const uint32_t keep = MODE == EDGE_ENC_EDGE ? 0xffffffffu : row_keep(m0);
                     uint32_t bb[16];
                     ldg256(p.b2h + c0, *reinterpret_cast<uint32_t(*)[8]>(&bb[0]));
                     ldg256(p.b2h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&bb[8]));
+                    mark(4, s);
                     mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                     tc_fence_after();
+                    mark(5, s);
 #pragma unroll
                     for (int g16 = 0; g16 < 2; ++g16) {
                         float acc[16];
@@ -342,7 +383,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         }
                         st16(T, g16, o);
                     }
-                    fence_async_smem(); tc_fence_before(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));
+                    mark(6, s);
+                    stage_done(s, true);
+                    mark(7, s);
                 }
                 rotate();
             }
@@ -352,6 +395,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             for (int s = 0; s < NSLOT; ++s) {
                 if (s < n) {
                     const TileMeta m = m0;
+                    mark(8, s);
                     m0 = load_meta(t0 + tile_stride + s);
                     if (MODE != EDGE_ENC_EDGE) {
                         mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
@@ -364,17 +408,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             for (int q = 0; q < MAX_NPT; ++q)
                                 if (q < nv) p.S[((size_t)meta_node0(m) + q) * 128 + r] = s4[q];
                         }
-                        tc_fence_before(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));     // accumulator drained: the slot's next MMA 1 may start
+                        stage_done(s, false);                            // accumulator drained: the slot's next MMA 1 may start
+                        mark(9, s);
                     } else {
                         unsigned char* T = sT + s * TILE_BYTES;
-                        const int node0 = meta_node0(m), bmem = node0 / p.L;
-                        const int in_row0 = p.in_is_frame ? (__ldg(p.frame_of + bmem) * p.L + (node0 - bmem * p.L)) * K : node0 * K;
-                        const __half* res_row = p.res + ((size_t)in_row0 + (r < meta_nv(m) * K ? r : 0)) * 128 + c0;
-                        uint32_t rs[16];
-                        ldg256_coherent(res_row, *reinterpret_cast<uint32_t(*)[8]>(&rs[0]));
-                        ldg256_coherent(res_row + 16, *reinterpret_cast<uint32_t(*)[8]>(&rs[8]));
+                        const int bmem = meta_node0(m) / p.L;
                         mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                         tc_fence_after();
+                        mbar_wait(smem_u32(&sBar[21 + s]), ph_res);              // the tile holds the original h_E rows again (residual)
+                        uint32_t rs[16];
+#pragma unroll
+                        for (int c16 = 0; c16 < 4; ++c16) {
+                            const uint4 t4 = *reinterpret_cast<const uint4*>(T + tile_off(r, (c0 >> 3) + c16));
+                            rs[c16 * 4] = t4.x; rs[c16 * 4 + 1] = t4.y; rs[c16 * 4 + 2] = t4.z; rs[c16 * 4 + 3] = t4.w;
+                        }
                         // pass A (fp32): v = residual + acc + b13, partial row statistics; v is parked as fp16 in the tile
                         float sum = 0.f, sq = 0.f;
 #pragma unroll
@@ -393,19 +440,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             }
                             st16(T, g16, o);
                         }
-                        // row statistics: the four column quarters of a row accumulate in shared memory.  64-bit fixed point
-                        // (2^-20 / 2^-16 resolution) keeps the sum associative, i.e. the result independent of arrival order.
-                        unsigned long long* st = sStat + r * 2;
-                        epi_sync();                                   // the previous stage's re-zeroing is complete
-                        atomicAdd(st, (unsigned long long)__float2ll_rn(sum * 1048576.0f));
-                        atomicAdd(st + 1, (unsigned long long)__float2ll_rn(sq * 65536.0f));
+                        // row statistics: the four column quarters of a row exchange their partial sums through accumulator
+                        // columns this thread has already drained (its own first two) -- tcgen05.st, one barrier, tcgen05.ld;
+                        // summed in a fixed order, so the result is deterministic
+                        tmem_st2(tmem_lane + (uint32_t)(s * 128), sum, sq);
                         tc_fence_before();
                         epi_sync();
-                        const float tsum = (float)(long long)st[0] * (1.0f / 1048576.0f), tsq = (float)(long long)st[1] * (1.0f / 65536.0f);
+                        tc_fence_after();
+                        float part[8];
+                        tmem_ld2_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128), 32u, part);
+                        const float tsum = (part[0] + part[2]) + (part[4] + part[6]), tsq = (part[1] + part[3]) + (part[5] + part[7]);
                         const float mean = tsum * (1.0f / 128.0f);
                         const float rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
-                        epi_sync();
-                        if (cq == 0) { st[0] = 0ull; st[1] = 0ull; }
                         const __half2 rstd2 = __float2half2_rn(rstd), mean2 = __float2half2_rn(mean);
                         const __half* mod_row = p.mod16 + (size_t)bmem * p.mod16_stride + c0;
                         // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
@@ -422,12 +468,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                                 o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
                             *slot = make_uint4(o[0], o[1], o[2], o[3]);
                         }
-                        fence_async_smem(); mbar_arrive(smem_u32(&sBar[3 + 3 * s]));   // tile complete: the TMA lane stores it and reloads the slot
+                        stage_done(s, true);                             // tile complete: the TMA lane stores it and reloads the slot
+                        mark(9, s);
                     }
                 }
                 rotate();
             }
             ph ^= 1;
+            ph_res ^= 1;
             ld_pc(m0, pcA);                                             // first E1 of the next round
             prefetch_pa(m0);
         }
@@ -439,7 +487,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 
 size_t tc_smem_bytes(int mode) {
     const int n_w = mode == EDGE_ENC_EDGE ? 3 : 2;
-    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 2048 : IND_BYTES) + 17 * 8 + 16;
+    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 0 : IND_BYTES) + 25 * 8 + 16;
 }
 
 }  // namespace

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     const uint32_t bar_full = smem_u32(&sBar[0]), bar_mma = smem_u32(&sBar[1]), bar_act = smem_u32(&sBar[2]);
     if (tid == 0) {
-        mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_act, NODE_EPI_THREADS);
+        mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_act, NODE_EPI_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 256) sStat[tid] = 0ull;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
         }
         const float* m = p.mod + (size_t)b * p.mod_stride + c0;
         float v[32];                                    // this thread's 32 columns of the row state, fp32
-        auto publish = [&]() { fence_async_smem(); tc_fence_before(); mbar_arrive(bar_act); };
+        auto publish = [&]() { fence_async_smem(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_act); };    // one arrival per warp
         auto wait_mma = [&]() { mbar_wait(bar_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); };
         auto store16 = [&](unsigned char* tile, int g16, const float* x) {     // 16 columns [c0 + 16 g16, +16) of row r as fp16
             uint32_t o[8];

@@ -24,7 +24,7 @@ a.record(); pl.run_edge_kernel(mode, 1); b.record(); torch.cuda.synchronize()
 print("kernel us", a.elapsed_time(b) * 1e3)
 tr = pl.buffer("tc_trace").cpu().tolist()
 n = tr[0]
-names = ["E1 loads issued", "E1 acc ready", "E2 loads issued", "E2 acc ready", "E3 begin", "E3 acc ready", "stage done"]
+names = ["E1 begin", "E1 acc ready", "E1 math done", "E1 handed off", "E2 begin", "E2 acc ready", "E2 math done", "E2 handed off", "E3 begin", "E3 done"]
 t0 = None
 prev = None
 for v in tr[1:1 + n]:
@@ -33,15 +33,4 @@ for v in tr[1:1 + n]:
     ev, s = code >> 2, code & 3
     if t0 is None: t0 = t
     print(f"{(t - t0) / 1000:8.2f} us  (+{0 if prev is None else (t - prev) / 1000:6.2f})  slot {s}  {names[ev]}")
-    prev = t
-
-print("---- control thread")
-n = tr[512]
-cn = ["S1 wait load", "S1 loaded", "S1 mma issued", "E1 wait", "E1 done seen", "MMA2 issued", "E2 wait", "E2 done seen", "RED issued", "RED complete", "next load issued", "E3 wait", "E3 done seen"]
-prev = None
-for v in tr[513:513 + n]:
-    v &= (1 << 64) - 1
-    t, code = v >> 8, v & 0xff
-    ev, s = code >> 2, code & 3
-    print(f"{(t - t0) / 1000:8.2f} us  (+{0 if prev is None else (t - prev) / 1000:6.2f})  slot {s}  {cn[ev]}")
     prev = t
