@@ -3,7 +3,7 @@
 //
 // One CTA = one tile of 128 nodes.  Warps 0-15 are the epilogue warps: thread (row r, column quarter cq) owns 32 of the
 // 128 columns of its node row (the four warps that can address a TMEM lane quarter split the columns); LayerNorm
-// row statistics are combined across the four quarters with order-independent fixed-point shared-memory atomics.
+// row statistics are exchanged between the four quarters through drained TMEM accumulator columns.
 // Warp 16 is the control warp: one lane streams the layer's fp16 weight blocks through four 32 KB shared-memory
 // slots with TMA and issues the tcgen05 MMAs.  The node kernels are latency chains (W3 -> LN -> FFN -> LN ->
 // projections), so the CTA alternates strictly between an MMA phase and an epilogue phase:
@@ -50,6 +50,7 @@ struct NodeTcParams {
     float* out6;
     const float *x_t, *noise, *coef;
     float* x_next;
+    unsigned long long* trace;   // debug timeline of CTA 0 (nullptr = off)
 };
 
 __device__ __forceinline__ void ldg_f32x8(const float* p, float* v) {
@@ -92,8 +93,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
     unsigned char* mid0 = hA + TILE_BYTES;            // FFN hidden block / h' of the decoder projections
     unsigned char* mid1 = mid0 + TILE_BYTES;
     unsigned char* sW = mid1 + TILE_BYTES;            // 4 weight slots
-    unsigned long long* sStat = reinterpret_cast<unsigned long long*>(sW + 4 * TILE_BYTES);   // [128 rows][sum, sum of squares], fixed point
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sStat + 256);              // [0] weights full, [1] mma done, [2] activations ready
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sW + 4 * TILE_BYTES);      // [0] weights full, [1] mma done, [2] activations ready
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
         mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_act, NODE_EPI_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 256) sStat[tid] = 0ull;
     if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(sTmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -118,6 +117,17 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
     if (warp == 16) {
         // ------------------------------------------------------------------ control warp
         if (lane == 0) {
+            unsigned long long* ctrace = (p.trace != nullptr && blockIdx.x == 0) ? p.trace + 512 : nullptr;
+            int n_ct = 0;
+            auto cmark = [&](int ev) {
+                if (ctrace != nullptr && n_ct < 400) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    ctrace[1 + n_ct] = (t << 8) | (unsigned long long)ev;
+                    ctrace[0] = (unsigned long long)(++n_ct);
+                }
+            };
+            cmark(0);
             uint32_t ph_full = 0, ph_mma = 0, ph_act = 0;
             auto load_weights = [&](const int* rows, int n) {
                 mbar_expect_tx(bar_full, (uint32_t)(n * TILE_BYTES));
@@ -143,8 +153,11 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
                 else if (kind == 3) { rows[n++] = p.wout_row + 256; rows[n++] = p.wout_row + 384; }
                 else { for (int j = 0; j < p.n_proj; ++j) { rows[n++] = p.proj[j].wa_row; rows[n++] = p.proj[j].wc_row; } }
                 load_weights(rows, n);                           // slots are free: the previous phase's MMAs have completed
+                cmark(1);
                 mbar_wait(bar_act, ph_act); ph_act ^= 1;         // operands written, accumulators drained
+                cmark(2);
                 mbar_wait(bar_full, ph_full); ph_full ^= 1;
+                cmark(3);
                 tc_fence_after();
                 if (kind == 0) { mma(hA, 0, 0, false); }
                 else if (kind == 1) { mma(hA, 0, 1, false); mma(hA, 1, 2, false); }
@@ -157,7 +170,9 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
                     }
                 }
                 umma_commit(bar_mma);
+                cmark(4);
                 mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;         // weight slots and operand tiles may be overwritten
+                cmark(5);
             }
         }
     } else {
@@ -169,23 +184,26 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
         uint32_t ph_mma = 0;
         int b = 0, zres = 0;
         float mk = 0.f, cnt = (float)p.K;
-        if (live) {
+        // per-row metadata (member, residue type, node mask, masked-neighbour count): dependent global loads, deliberately
+        // issued AFTER the first operand stage so they do not delay the first MMA
+        auto load_row_meta = [&]() {
+            if (!live) return;
             b = n / p.L;
             const int i = n - b * p.L;
-            const int f = p.frame_of[b];
-            const int len = p.lengths[f];
+            const int f = __ldg(p.frame_of + b);
+            const int len = __ldg(p.lengths + f);
             mk = i < len ? 1.f : 0.f;
-            zres = p.cg_z[(size_t)f * p.L + i];
+            zres = __ldg(p.cg_z + (size_t)f * p.L + i);
             if (p.masked_count && len < p.L) {
                 int cn = 0;
                 if (i < len) {
                     const int* row = p.nbr_idx + ((size_t)f * p.L + i) * p.K;
-                    for (int k = 0; k < p.K; ++k) cn += row[k] < len ? 1 : 0;
+                    for (int k = 0; k < p.K; ++k) cn += __ldg(row + k) < len ? 1 : 0;
                 }
                 cnt = (float)cn;
             }
-        }
-        const float* m = p.mod + (size_t)b * p.mod_stride + c0;
+        };
+        const float* m = p.mod + (size_t)(live ? n / p.L : 0) * p.mod_stride + c0;
         float v[32];                                    // this thread's 32 columns of the row state, fp32
         auto publish = [&]() { fence_async_smem(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_act); };    // one arrival per warp
         auto wait_mma = [&]() { mbar_wait(bar_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); };
@@ -196,22 +214,22 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
             *reinterpret_cast<uint4*>(tile + tile_off(r, (c0 >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(tile + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         };
-        // LayerNorm statistics of the full row (no affine, eps 1e-6): the four column quarters combine their partial sums
-        // in shared memory with 64-bit fixed-point atomics (associative -> the result does not depend on arrival order)
-        auto row_stats = [&](float& mean, float& rstd) {
+        // LayerNorm statistics of the full row (no affine, eps 1e-6): the four column quarters of a row exchange their partial
+        // sums through accumulator columns this thread has just drained (`region`): tcgen05.st, one barrier, tcgen05.ld; the
+        // four partials are summed in a fixed order, so the result is deterministic
+        auto row_stats = [&](int region, float& mean, float& rstd) {
             float sum = 0.f, sq = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; ++c) { sum += v[c]; sq = fmaf(v[c], v[c], sq); }
-            unsigned long long* st = sStat + r * 2;
-            node_epi_sync();                            // the previous use has been re-zeroed
-            atomicAdd(st, (unsigned long long)__float2ll_rn(sum * 1048576.0f));
-            atomicAdd(st + 1, (unsigned long long)__float2ll_rn(sq * 65536.0f));
+            tmem_st2(tmem_lane + (uint32_t)(region * 128), sum, sq);
+            tc_fence_before();
             node_epi_sync();
-            const float tsum = (float)(long long)st[0] * (1.0f / 1048576.0f), tsq = (float)(long long)st[1] * (1.0f / 65536.0f);
+            tc_fence_after();
+            float part[8];
+            tmem_ld2_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(region * 128), 32u, part);
+            const float tsum = (part[0] + part[2]) + (part[4] + part[6]), tsq = (part[1] + part[3]) + (part[5] + part[7]);
             mean = tsum * (1.0f / 128.0f);
             rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
-            node_epi_sync();
-            if (cq == 0) { st[0] = 0ull; st[1] = 0ull; }
         };
 
         if (p.do_update) {
@@ -229,6 +247,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
                 store16(hA, 0, s32); store16(hA, 1, s32 + 16);
             }
             publish();
+            load_row_meta();
             // ---- EA: h1 = gate1 * (LN(h_V + (acc + cnt b3)/30) (1 + scale1) + shift1) ----
             wait_mma();
 #pragma unroll
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
             }
             {
                 float mean, rstd;
-                row_stats(mean, rstd);
+                row_stats(0, mean, rstd);
                 float sh[32], sc[32], gt[32];
                 ld32(m, sh); ld32(m + 128, sc); ld32(m + 256, gt);
 #pragma unroll
@@ -285,13 +304,14 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
             }
             {
                 float mean, rstd;
-                row_stats(mean, rstd);
+                row_stats(3, mean, rstd);
                 float sh[32], sc[32], gt[32];
                 ld32(m + 384, sh); ld32(m + 512, sc); ld32(m + 640, gt);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = mk * (gt[c] * fmaf((v[c] - mean) * rstd, 1.0f + sc[c], sh[c]));
             }
         } else {
+            load_row_meta();
             // ---- node init: h = x_in(x) ----
             float x0 = 0.f, x1 = 0.f, x2 = 0.f;
             if (live) { x0 = p.x[(size_t)n * 3]; x1 = p.x[(size_t)n * 3 + 1]; x2 = p.x[(size_t)n * 3 + 2]; }
@@ -406,7 +426,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
     if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-constexpr size_t NODE_TC_SMEM = 7 * (size_t)TILE_BYTES + 2048 + 64;
+constexpr size_t NODE_TC_SMEM = 7 * (size_t)TILE_BYTES + 64;
 
 struct NodeTcState { CUtensorMap wmap; };
 
@@ -423,6 +443,7 @@ void base_params(Plan& p, NodeTcParams& np) {
     np.N = p.NB * p.L; np.L = p.L; np.K = p.K;
     np.lengths = p.lengths; np.frame_of = p.frame_of; np.nbr_idx = p.nbr_idx; np.cg_z = p.cg_z;
     np.hV = p.hV; np.hVenc = p.hVenc; np.S = p.S;
+    np.trace = p.tc_trace;
 }
 
 }  // namespace
