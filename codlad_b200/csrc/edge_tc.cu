@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     // barriers: [0] weights; per tile slot g: [1+3g] load (TMA tx), [2+3g] acc (MMA commit), [3+3g] epi (16 warp arrivals); [13+g] go;
     // ENC_EDGE: [17+g] MMA 3 complete (operand tile reusable), [21+g] residual re-load landed
     uint64_t* sBar = reinterpret_cast<uint64_t*>(sAux + (MODE == EDGE_ENC_EDGE ? 0 : IND_BYTES));
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 25);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 29);
 
     const int tid = threadIdx.x;
     const int K = p.K, NPT = p.NPT;
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             mbar_init(smem_u32(&sBar[13 + g]), 1);
             mbar_init(smem_u32(&sBar[17 + g]), 1);
             mbar_init(smem_u32(&sBar[21 + g]), 1);
+            mbar_init(smem_u32(&sBar[25 + g]), 4);                     // ENC_NODE / DEC: accumulator drained (the 4 warps of column quarter 0)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -238,13 +239,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 // ENC_EDGE recycles the operand tile only now (store, then reload), so its MMA 1 trails by one slot.
                 const uint32_t next_parity = (round + 1) & 1;
                 for (int g = 0; g < n; ++g) {
-                    mbar_wait(bar_epi(g), ph_epi);
-                    if (MODE == EDGE_ENC_EDGE) mbar_arrive(bar_go(g));                                         // tile complete in smem: store + recycle
+                    if (MODE == EDGE_ENC_EDGE) {
+                        mbar_wait(bar_epi(g), ph_epi);
+                        mbar_arrive(bar_go(g));                                                                // tile complete in smem: store + recycle
+                    } else {
+                        mbar_wait(smem_u32(&sBar[25 + g]), round & 1);                                         // reduced sums read out of TMEM
+                    }
                     const int h = MODE == EDGE_ENC_EDGE ? g - 1 : g;
                     if (h >= 0 && h < n_next) { mbar_wait(bar_load(h), next_parity); issue_mma(h, 0); }
                 }
                 if (MODE == EDGE_ENC_EDGE && n - 1 < n_next) { mbar_wait(bar_load(n - 1), next_parity); issue_mma(n - 1, 0); }
-                ph_epi ^= 1;
+                if (MODE == EDGE_ENC_EDGE) ph_epi ^= 1;
             }
         }
     } else {
@@ -321,6 +326,28 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         uint32_t pcA[16], pcB[16];                                      // gathered halves, double buffered one stage ahead
         ld_pc(m0, pcA);
 
+        // ENC_NODE / DEC: "E3" (read the reduced sums out of TMEM, store S, release the accumulator, fetch the slot's next
+        // metadata) is not a stage of its own: it rides at the tail of the FOLLOWING stage, when the (short) reduction MMA
+        // has long completed, so nothing waits on it.  Operates on m3 = the slot processed one stage ago.
+        auto drain = [&](int s, int next_tile) {
+            const TileMeta m = m3;
+            m3 = load_meta(next_tile);
+            if (cq == 0) {                                               // one warp per scheduler; the other twelve run ahead into the next stage
+                mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph ^ 1);           // third commit of the tile (reduction MMA)
+                tc_fence_after();
+                float s4[4];
+                tmem_ld4(tmem_lane + (uint32_t)(s * 128), s4);          // lane = output column, 4 columns = nodes of the tile
+                const int nv = meta_nv(m);
+#pragma unroll
+                for (int q = 0; q < MAX_NPT; ++q)
+                    if (q < nv) p.S[((size_t)meta_node0(m) + q) * 128 + r] = s4[q];
+                tc_fence_before();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(smem_u32(&sBar[25 + s]));   // accumulator drained: the slot's next MMA 1 may start
+            }
+        };
+        bool pending3 = false;                                           // slot 3 of the previous round still has to be drained
+
         for (int t0 = blockIdx.x * NSLOT; t0 < p.n_tiles; t0 += tile_stride) {
             const int n = min(NSLOT, p.n_tiles - t0);                   // live slots of this round
             // ================= E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile
@@ -353,6 +380,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 #pragma unroll 1
             for (int s2 = 0; s2 < NSLOT; s2 += 2) {
                 if (s2 < n) { if (s2 + 1 < n) { ld_pc(m1, pcB); prefetch_pa(m1); } epi1(s2, pcA); }
+                if (MODE != EDGE_ENC_EDGE && s2 == 0 && pending3) { drain(3, t0 + 3); pending3 = false; }
                 rotate();
                 if (s2 + 1 < n) { if (s2 + 2 < n) { ld_pc(m1, pcA); prefetch_pa(m1); } epi1(s2 + 1, pcB); }
                 rotate();
@@ -387,30 +415,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     stage_done(s, true);
                     mark(7, s);
                 }
+                if (MODE != EDGE_ENC_EDGE && s >= 1 && s - 1 < n) drain(s - 1, t0 + tile_stride + s - 1);
                 rotate();
             }
+            if (MODE != EDGE_ENC_EDGE) pending3 = n == NSLOT;
             ph ^= 1;
-            // ================= E3: finish the tile; fetch the metadata (and the first Pc) of the slot's next tile
+            // ================= E3 (ENC_EDGE): residual + LayerNorm + adaLN; fetch the metadata of the slot's next tile
 #pragma unroll 1
             for (int s = 0; s < NSLOT; ++s) {
-                if (s < n) {
+                if (MODE == EDGE_ENC_EDGE && s < n) {
                     const TileMeta m = m0;
                     mark(8, s);
                     m0 = load_meta(t0 + tile_stride + s);
-                    if (MODE != EDGE_ENC_EDGE) {
-                        mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
-                        tc_fence_after();
-                        if (cq == 0) {
-                            float s4[4];
-                            tmem_ld4(tmem_lane + (uint32_t)(s * 128), s4);      // lane = output column, 4 columns = nodes of the tile
-                            const int nv = meta_nv(m);
-#pragma unroll
-                            for (int q = 0; q < MAX_NPT; ++q)
-                                if (q < nv) p.S[((size_t)meta_node0(m) + q) * 128 + r] = s4[q];
-                        }
-                        stage_done(s, false);                            // accumulator drained: the slot's next MMA 1 may start
-                        mark(9, s);
-                    } else {
+                    {
                         unsigned char* T = sT + s * TILE_BYTES;
                         const int bmem = meta_node0(m) / p.L;
                         mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
@@ -472,13 +489,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         mark(9, s);
                     }
                 }
-                rotate();
+                if (MODE == EDGE_ENC_EDGE) rotate();
             }
             ph ^= 1;
             ph_res ^= 1;
             ld_pc(m0, pcA);                                             // first E1 of the next round
             prefetch_pa(m0);
         }
+        if (MODE != EDGE_ENC_EDGE && pending3) drain(3, p.n_tiles);        // (ph ^ 1 inside drain = the last round's third parity)
     }
     tc_fence_before();
     __syncthreads();
@@ -487,7 +505,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 
 size_t tc_smem_bytes(int mode) {
     const int n_w = mode == EDGE_ENC_EDGE ? 3 : 2;
-    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 0 : IND_BYTES) + 25 * 8 + 16;
+    return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 0 : IND_BYTES) + 29 * 8 + 16;
 }
 
 }  // namespace
