@@ -196,13 +196,14 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         off[k + "W13_t"] = pk.transposed(w13, H, H, 0, H); off[k + "b13"] = pk.copy(b13, H);
         off[k + "Win_t"] = pk.transposed(win, 4 * H, H, 0, H); off[k + "bin"] = pk.copy(bin, 4 * H);
         off[k + "Wout_t"] = pk.transposed(wout, H, 4 * H, 0, 4 * H); off[k + "bout"] = pk.copy(bout, H);
-        boff[k + "W1b"] = bp.block(w1, 3 * H, H); boff[k + "W2"] = bp.block(w2, H, 0);
-        boff[k + "W11b"] = bp.block(w11, 3 * H, H); boff[k + "W12"] = bp.block(w12, H, 0); boff[k + "W13"] = bp.block(w13, H, 0);
+        // fp16 blocks that consume a GELU activation are packed x 0.5: the tensor-core epilogues emit 2 GELU (tc_common.cuh)
+        boff[k + "W1b"] = bp.block(w1, 3 * H, H); boff[k + "W2"] = bp.block(w2, H, 0, 0.5f);
+        boff[k + "W11b"] = bp.block(w11, 3 * H, H); boff[k + "W12"] = bp.block(w12, H, 0, 0.5f); boff[k + "W13"] = bp.block(w13, H, 0, 0.5f);
         boff[k + "W1a"] = bp.block(w1, 3 * H, 0); boff[k + "W1c"] = bp.block(w1, 3 * H, 2 * H);
         boff[k + "W11a"] = bp.block(w11, 3 * H, 0); boff[k + "W11c"] = bp.block(w11, 3 * H, 2 * H);
         boff[k + "W3"] = bp.block(w3, H, 0);
         for (int q = 0; q < 4; ++q) { size_t o = bp.block(win + (size_t)q * H * H, H, 0); if (q == 0) boff[k + "Win"] = o; }
-        for (int q = 0; q < 4; ++q) { size_t o = bp.block(wout, 4 * H, q * H); if (q == 0) boff[k + "Wout"] = o; }
+        for (int q = 0; q < 4; ++q) { size_t o = bp.block(wout, 4 * H, q * H, 0.5f); if (q == 0) boff[k + "Wout"] = o; }
     }
     for (int l = 0; l < 3; ++l) {
         const std::string p = "decoder_layers." + std::to_string(l), k = "d" + std::to_string(l) + ".";
@@ -226,11 +227,11 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         off[k + "W3_t"] = pk.transposed(w3, H, H, 0, H); off[k + "b3"] = pk.copy(b3, H);
         off[k + "Win_t"] = pk.transposed(win, 4 * H, H, 0, H); off[k + "bin"] = pk.copy(bin, 4 * H);
         off[k + "Wout_t"] = pk.transposed(wout, H, 4 * H, 0, 4 * H); off[k + "bout"] = pk.copy(bout, H);
-        boff[k + "W1b2"] = bp.block(w1, 4 * H, H, 2.0f); boff[k + "W2"] = bp.block(w2, H, 0);
+        boff[k + "W1b2"] = bp.block(w1, 4 * H, H, 2.0f); boff[k + "W2"] = bp.block(w2, H, 0, 0.5f);
         boff[k + "W1a"] = bp.block(w1, 4 * H, 0); boff[k + "W1d"] = bp.block(w1, 4 * H, 3 * H);
         boff[k + "W3"] = bp.block(w3, H, 0);
         for (int q = 0; q < 4; ++q) { size_t o = bp.block(win + (size_t)q * H * H, H, 0); if (q == 0) boff[k + "Win"] = o; }
-        for (int q = 0; q < 4; ++q) { size_t o = bp.block(wout, 4 * H, q * H); if (q == 0) boff[k + "Wout"] = o; }
+        for (int q = 0; q < 4; ++q) { size_t o = bp.block(wout, 4 * H, q * H, 0.5f); if (q == 0) boff[k + "Wout"] = o; }
     }
     GET(finw, "W_out.linear.weight", 6 * H) GET(finb, "W_out.linear.bias", 6)
     off["fin_w_t"] = pk.transposed(finw, 6, H, 0, H); off["fin_b"] = pk.copy(finb, 6);

@@ -66,12 +66,11 @@ constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 K
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the epilogue threads only
 
 // per-thread view of a tile, packed into two registers (four of them are live; they rotate so that the stage code
-// exists once):  a = node0 | q_of_row << 26 | nv << 28 ;  b = member-local neighbour index j (raw: nothing waits on its load
-// until the next round's E1), or 0x80000000 for a row outside the tile
+// exists once):  a = member << 16 | tile-within-member (advanced without divisions) ;  b = member-local neighbour index j
+// (raw: nothing waits on its load until the next round's E1), or 0x80000000 for a row outside the tile
 struct TileMeta { uint32_t a, b; };
-__device__ __forceinline__ int meta_node0(const TileMeta& m) { return (int)(m.a & 0x3ffffffu); }
-__device__ __forceinline__ int meta_q(const TileMeta& m) { return (int)((m.a >> 26) & 3u); }
-__device__ __forceinline__ int meta_nv(const TileMeta& m) { return (int)(m.a >> 28); }
+__device__ __forceinline__ int meta_member(const TileMeta& m) { return (int)(m.a >> 16); }
+__device__ __forceinline__ int meta_tin(const TileMeta& m) { return (int)(m.a & 0xffffu); }
 __device__ __forceinline__ int meta_j(const TileMeta& m) { return (int)(m.b & 0x7fffffffu); }
 __device__ __forceinline__ bool meta_row_valid(const TileMeta& m) { return (int)m.b >= 0; }
 
@@ -112,15 +111,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (MODE != EDGE_ENC_EDGE) {
-        // indicator B operand of the reduction MMA: Ind[q][r] = 1 if row r belongs to node q (K-major SW128, 16 rows x 128 k)
+        // indicator B operand of the reduction MMA: Ind[q][r] = 1/2 if row r belongs to node q (K-major SW128, 16 rows x 128 k)
         for (int t = tid; t < 16 * 16; t += CTA_THREADS) {
             const int q = t >> 4, c16 = t & 15;
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int r0 = c16 * 8 + e * 2;
-                const __half lo = __float2half((q < NPT && r0 / K == q) ? 1.f : 0.f);
-                const __half hi = __float2half((q < NPT && (r0 + 1) / K == q) ? 1.f : 0.f);
+                const __half lo = __float2half((q < NPT && r0 / K == q) ? 0.5f : 0.f);        // 0.5: the activations are 2 GELU
+                const __half hi = __float2half((q < NPT && (r0 + 1) / K == q) ? 0.5f : 0.f);
                 w[e] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
             }
             const uint32_t off = (uint32_t)((c16 >> 3) * (16 * 128) + q * 128 + (((c16 & 7) ^ (q & 7)) << 4));
@@ -268,37 +267,41 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             if ((tid & 31) == 0) mbar_arrive(smem_u32(&sBar[3 + 3 * s]));
         };
 
-        // metadata of tile `tile` for this thread (global loads; consumed a full round later)
-        auto load_meta = [&](int tile) {
-            TileMeta m{0u, 0u};
-            if (tile >= p.n_tiles) return m;
-            const int b = tile / p.tiles_per_member;
-            const int i0 = (tile - b * p.tiles_per_member) * NPT;
-            const int nv = min(NPT, p.L - i0);
+        // metadata of a tile for this thread (one global load, consumed a full round later).  (member, tile-in-member) advance
+        // by a fixed step per round, so there is no integer division on the per-tile path.
+        const int step_b = tile_stride / p.tiles_per_member, step_t = tile_stride - step_b * p.tiles_per_member;
+        auto make_meta = [&](int tile, int b, int tin) {
+            TileMeta m{((uint32_t)b << 16) | (uint32_t)tin, 0x80000000u};
+            if (tile >= p.n_tiles) { m.a = 0u; return m; }              // past the end: keep every derived address in bounds
+            const int i0 = tin * NPT;
             const int f = p.single_frame ? 0 : __ldg(p.frame_of + b);    // (dependent load only for multi-frame plans)
-            int qq = 0;
-            m.b = 0x80000000u;
-            if (q_of_r < nv) {
-                qq = q_of_r;
+            if (q_of_r < min(NPT, p.L - i0))
                 m.b = (uint32_t)__ldg(p.nbr_idx + ((size_t)f * p.L + i0 + q_of_r) * K + (r - q_of_r * K));
-            }
-            m.a = (uint32_t)(b * p.L + i0) | ((uint32_t)qq << 26) | ((uint32_t)nv << 28);
             return m;
         };
+        auto first_meta = [&](int tile) {
+            const int b = tile / p.tiles_per_member;
+            return make_meta(tile, b, tile - b * p.tiles_per_member);
+        };
+        auto next_meta = [&](const TileMeta& m, int tile) {               // the slot's tile of the next round
+            int b = meta_member(m) + step_b, tin = meta_tin(m) + step_t;
+            if (tin >= p.tiles_per_member) { tin -= p.tiles_per_member; ++b; }
+            return make_meta(tile, b, tin);
+        };
+        auto node0_of = [&](const TileMeta& m) { return meta_member(m) * p.L + meta_tin(m) * NPT; };
+        auto nv_of = [&](const TileMeta& m) { return min(NPT, p.L - meta_tin(m) * NPT); };
         auto prefetch_pa = [&](const TileMeta& m) {                     // pull the own-half segment of the next stage into L1
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P16 + (size_t)(meta_node0(m) + meta_q(m)) * 256 + c0));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P16 + (size_t)(node0_of(m) + (meta_row_valid(m) ? q_of_r : 0)) * 256 + c0));
         };
         // neighbour-sum mask of this thread's row (reference: mask_attend = mask_i mask_j; the decoder passes no mask)
         auto row_keep = [&](const TileMeta& m) -> uint32_t {
             if (!meta_row_valid(m)) return 0u;
             if (MODE == EDGE_DEC) return 0xffffffffu;
-            const int node0 = meta_node0(m), b = node0 / p.L;
-            const int len = p.single_frame ? len0 : __ldg(p.lengths + __ldg(p.frame_of + b));
-            return (node0 - b * p.L + meta_q(m) < len && meta_j(m) < len) ? 0xffffffffu : 0u;
+            const int len = p.single_frame ? len0 : __ldg(p.lengths + __ldg(p.frame_of + meta_member(m)));
+            return (meta_tin(m) * NPT + q_of_r < len && meta_j(m) < len) ? 0xffffffffu : 0u;
         };
         auto ld_pc = [&](const TileMeta& m, uint32_t (&pc)[16]) {       // this thread's 32 gathered halves of Pc[j]
-            const int b = meta_node0(m) / p.L;
-            const __half* src = p.P16 + ((size_t)b * p.L + meta_j(m)) * 256 + 128 + c0;
+            const __half* src = p.P16 + ((size_t)meta_member(m) * p.L + meta_j(m)) * 256 + 128 + c0;
             ldg256(src, *reinterpret_cast<uint32_t(*)[8]>(&pc[0]));
             ldg256(src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[8]));
         };
@@ -318,8 +321,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 trace[0] = (unsigned long long)(++n_trace);
             }
         };
-        TileMeta m0 = load_meta(blockIdx.x * NSLOT + 0), m1 = load_meta(blockIdx.x * NSLOT + 1),
-                 m2 = load_meta(blockIdx.x * NSLOT + 2), m3 = load_meta(blockIdx.x * NSLOT + 3);
+        TileMeta m0 = first_meta(blockIdx.x * NSLOT + 0), m1 = first_meta(blockIdx.x * NSLOT + 1),
+                 m2 = first_meta(blockIdx.x * NSLOT + 2), m3 = first_meta(blockIdx.x * NSLOT + 3);
         auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
         uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
@@ -331,16 +334,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         // has long completed, so nothing waits on it.  Operates on m3 = the slot processed one stage ago.
         auto drain = [&](int s, int next_tile) {
             const TileMeta m = m3;
-            m3 = load_meta(next_tile);
+            m3 = next_meta(m, next_tile);
             if (cq == 0) {                                               // one warp per scheduler; the other twelve run ahead into the next stage
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph ^ 1);           // third commit of the tile (reduction MMA)
                 tc_fence_after();
                 float s4[4];
                 tmem_ld4(tmem_lane + (uint32_t)(s * 128), s4);          // lane = output column, 4 columns = nodes of the tile
-                const int nv = meta_nv(m);
+                const int nv = nv_of(m), node0 = node0_of(m);
 #pragma unroll
                 for (int q = 0; q < MAX_NPT; ++q)
-                    if (q < nv) p.S[((size_t)meta_node0(m) + q) * 128 + r] = s4[q];
+                    if (q < nv) p.S[((size_t)node0 + q) * 128 + r] = s4[q];
                 tc_fence_before();
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(smem_u32(&sBar[25 + s]));   // accumulator drained: the slot's next MMA 1 may start
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             auto epi1 = [&](int s, const uint32_t (&pc)[16]) {
                 unsigned char* T = sT + s * TILE_BYTES;
                 uint32_t pa[16];
-                const __half* pa_src = p.P16 + (size_t)(meta_node0(m0) + meta_q(m0)) * 256 + c0;
+                const __half* pa_src = p.P16 + (size_t)(node0_of(m0) + (meta_row_valid(m0) ? q_of_r : 0)) * 256 + c0;
                 ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
                 ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
                 mark(0, s);
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(pa[g16 * 8 + e])), as_h2(pc[g16 * 8 + e]));
-                        o[e] = as_u32(gelu_h2(x));
+                        o[e] = as_u32(gelu2_h2(x));
                     }
                     st16(T, g16, o);
                 }
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const __half2 x = __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(bb[g16 * 8 + e]));
-                            o[e] = as_u32(gelu_h2(x)) & keep;
+                            o[e] = as_u32(gelu2_h2(x)) & keep;
                         }
                         st16(T, g16, o);
                     }
@@ -426,10 +429,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 if (MODE == EDGE_ENC_EDGE && s < n) {
                     const TileMeta m = m0;
                     mark(8, s);
-                    m0 = load_meta(t0 + tile_stride + s);
+                    m0 = next_meta(m, t0 + tile_stride + s);
                     {
                         unsigned char* T = sT + s * TILE_BYTES;
-                        const int bmem = meta_node0(m) / p.L;
+                        const int bmem = meta_member(m);
                         mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                         tc_fence_after();
                         mbar_wait(smem_u32(&sBar[21 + s]), ph_res);              // the tile holds the original h_E rows again (residual)
@@ -538,6 +541,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     const TcMaps& maps = *reinterpret_cast<const TcMaps*>(p.tmaps);
     TcParams tp{};
     tp.L = p.L; tp.K = p.K;
+    if (p.NB > 65535 || p.L > 65535) { set_error("edge_tc: NB=%d / L=%d exceed the 16-bit tile metadata fields", p.NB, p.L); return 1; }
     tp.NPT = 128 / p.K < MAX_NPT ? 128 / p.K : MAX_NPT;
     if (tp.NPT < 1 || p.K % 8 != 0) tp.NPT = 1;      // node row blocks must start on a swizzle-atom (8-row) boundary
     tp.tiles_per_member = (p.L + tp.NPT - 1) / tp.NPT;

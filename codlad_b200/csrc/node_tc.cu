@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
                         tmem_ld16(tmem_lane + (uint32_t)((1 + blk) * 128 + g16 * 16), acc);
                         uint32_t o[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = as_u32(gelu_h2(as_h2(pack_sat(acc[e * 2] + bb[e * 2], acc[e * 2 + 1] + bb[e * 2 + 1]))));
+                        for (int e = 0; e < 8; ++e) o[e] = as_u32(gelu2_h2(as_h2(pack_sat(acc[e * 2] + bb[e * 2], acc[e * 2 + 1] + bb[e * 2 + 1]))));
                         *reinterpret_cast<uint4*>(dst + tile_off(r, (c0 >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<uint4*>(dst + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
