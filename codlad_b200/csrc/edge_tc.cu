@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     const int tid = threadIdx.x;
     const int K = p.K, NPT = p.NPT;
     if ((smem_u32(smem) & 1023u) != 0) __trap();                                   // SWIZZLE_128B atoms repeat every 1 KiB
+    pdl_launch_dependents();               // the next kernel of the step may start its prologue on SMs this grid leaves idle
 
     // ---- one-time setup: barriers, TMEM, indicator operand ----
     if (tid == 0) {
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 out_row0[g] = (b * p.L + i0) * K;
                 issue_rows(g, bar_load(g));
             };
+            pdl_wait();                                               // h_E is produced by the previous kernels of the step
             for (int g = 0; g < 4; ++g)
                 if (blockIdx.x * 4 + g < p.n_tiles) issue_load(g, blockIdx.x * 4 + g);
             uint32_t ph_go = 0;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
         uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
         uint32_t pcA[16], pcB[16];                                      // gathered halves, double buffered one stage ahead
+        pdl_wait();                                                     // P16 / S / h_E belong to the previous kernels of the step
         ld_pc(m0, pcA);
 
         // ENC_NODE / DEC: "E3" (read the reduced sums out of TMEM, store S, release the accumulator, fetch the slot's next
@@ -571,9 +574,9 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
         tp.w_row[0] = row_of(d.W1b2_h); tp.w_row[1] = row_of(d.W2_h); tp.b2h = d.b2_16;
     }
     const int grid = min(p.num_sms, (tp.n_tiles + 3) / 4);
-    if (mode == EDGE_ENC_NODE) edge_tc_kernel<EDGE_ENC_NODE><<<grid, CTA_THREADS, tc_smem_bytes(mode), s>>>(maps, tp);
-    else if (mode == EDGE_ENC_EDGE) edge_tc_kernel<EDGE_ENC_EDGE><<<grid, CTA_THREADS, tc_smem_bytes(mode), s>>>(maps, tp);
-    else edge_tc_kernel<EDGE_DEC><<<grid, CTA_THREADS, tc_smem_bytes(mode), s>>>(maps, tp);
+    if (mode == EDGE_ENC_NODE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_NODE>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
+    else if (mode == EDGE_ENC_EDGE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_EDGE>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
+    else CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_DEC>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
     CB2_LAUNCH_CHECK();
     p.launches++;
     return 0;

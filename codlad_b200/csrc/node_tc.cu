@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
+    pdl_launch_dependents();               // the next kernel of the step may start its prologue on the SMs this grid leaves idle
     const uint32_t bar_full = smem_u32(&sBar[0]), bar_mma = smem_u32(&sBar[1]), bar_act = smem_u32(&sBar[2]);
     if (tid == 0) {
         mbar_init(bar_full, 1); mbar_init(bar_mma, 1); mbar_init(bar_act, NODE_EPI_THREADS / 32);
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
         };
         const float* m = p.mod + (size_t)(live ? n / p.L : 0) * p.mod_stride + c0;
         float v[32];                                    // this thread's 32 columns of the row state, fp32
+        pdl_wait();                                     // S / h_V / x are produced by the previous kernels of the step
         auto publish = [&]() { fence_async_smem(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_act); };    // one arrival per warp
         auto wait_mma = [&]() { mbar_wait(bar_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); };
         auto store16 = [&](unsigned char* tile, int g16, const float* x) {     // 16 columns [c0 + 16 g16, +16) of row r as fp16
@@ -432,7 +434,7 @@ struct NodeTcState { CUtensorMap wmap; };
 
 int node_tc_launch(Plan& p, NodeTcParams& np, cudaStream_t s) {
     const NodeTcState& st = *reinterpret_cast<const NodeTcState*>(p.node_tc);
-    node_tc_kernel<<<(np.N + 127) / 128, NODE_EPI_THREADS + 32, NODE_TC_SMEM, s>>>(st.wmap, np);
+    CB2_CUDA(launch_pdl(node_tc_kernel, dim3((np.N + 127) / 128), dim3(NODE_EPI_THREADS + 32), NODE_TC_SMEM, s, st.wmap, np));
     CB2_LAUNCH_CHECK();
     p.launches++;
     return 0;

@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace cb2 {
@@ -177,6 +179,23 @@ __device__ __forceinline__ __half2 gelu2_h2(__half2 x) {
     return __hfma2(x, as_h2(t), x);
 }
 
+
+// Programmatic dependent launch: the kernels of the step loop are launched with programmatic stream serialisation, call
+// pdl_launch_dependents() at their start (so the NEXT kernel's CTAs can be scheduled on idle SMs and run their prologue --
+// barrier init, TMEM allocation, weight TMA) and pdl_wait() before the first access to memory the previous kernel produces.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
