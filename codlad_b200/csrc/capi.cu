@@ -252,6 +252,7 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
             const std::string pe = "encoder_layers." + std::to_string(l), pd = "decoder_layers." + std::to_string(l);
             putv("e" + std::to_string(l) + ".b2", tt.get(pe + ".W2.bias", H));
             putv("e" + std::to_string(l) + ".b12", tt.get(pe + ".W12.bias", H));
+            putv("e" + std::to_string(l) + ".b13", tt.get(pe + ".W13.bias", H));
             putv("d" + std::to_string(l) + ".b2", tt.get(pd + ".W2.bias", H));
         }
         CB2_CUDA(cudaMalloc(&m.dev_vec16, v16.size() * sizeof(__half)));
@@ -259,6 +260,7 @@ int cb2_denoiser_create(const cb2_tensor* tensors, int n_tensors, const float* f
         for (int l = 0; l < 3; ++l) {
             m.enc[l].b2_16 = m.dev_vec16 + voff.at("e" + std::to_string(l) + ".b2");
             m.enc[l].b12_16 = m.dev_vec16 + voff.at("e" + std::to_string(l) + ".b12");
+            m.enc[l].b13_16 = m.dev_vec16 + voff.at("e" + std::to_string(l) + ".b13");
             m.dec[l].b2_16 = m.dev_vec16 + voff.at("d" + std::to_string(l) + ".b2");
         }
     }

@@ -49,7 +49,7 @@ struct TcParams {
     int n_w;                         // 2 (ENC_NODE / DEC) or 3 (ENC_EDGE)
     const __half* P16;               // [N, 256] fp16: [own half Wa h_V_i + b1 | gathered half Wc h_V_j (+ decoder table)]
     const __half* b2h;               // [128] second-layer bias, fp16
-    const float* b3;                 // [128] third-layer bias (ENC_EDGE), fp32
+    const __half* b3h;               // [128] third-layer bias (ENC_EDGE), fp16
     const __half* mod16;             // ENC_EDGE: [rows, 3, 256] gate (1 + scale) | gate * shift; member row at b * mod16_stride
     int mod16_stride;
     const __half* res;               // ENC_EDGE: residual source (= the tile's input rows)
@@ -339,8 +339,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             const TileMeta m = m3;
             m3 = next_meta(m, next_tile);
             if (cq == 0) {                                               // one warp per scheduler; the other twelve run ahead into the next stage
+                mark(8, s);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph ^ 1);           // third commit of the tile (reduction MMA)
                 tc_fence_after();
+                mark(9, s);
                 float s4[4];
                 tmem_ld4(tmem_lane + (uint32_t)(s * 128), s4);          // lane = output column, 4 columns = nodes of the tile
                 const int nv = nv_of(m), node0 = node0_of(m);
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 tc_fence_before();
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(smem_u32(&sBar[25 + s]));   // accumulator drained: the slot's next MMA 1 may start
+                mark(10, s);
             }
         };
         bool pending3 = false;                                           // slot 3 of the previous round still has to be drained
@@ -367,10 +370,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                 tc_fence_after();
                 mark(1, s);
+                float acc0[16], acc1[16];
+                tmem_ld16x2(tmem_lane + (uint32_t)(s * 128), acc0, acc1);
 #pragma unroll
                 for (int g16 = 0; g16 < 2; ++g16) {
-                    float acc[16];
-                    tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
+                    const float (&acc)[16] = g16 ? acc1 : acc0;
                     uint32_t o[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -405,10 +409,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                     tc_fence_after();
                     mark(5, s);
+                    float acc0[16], acc1[16];
+                    tmem_ld16x2(tmem_lane + (uint32_t)(s * 128), acc0, acc1);
 #pragma unroll
                     for (int g16 = 0; g16 < 2; ++g16) {
-                        float acc[16];
-                        tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
+                        const float (&acc)[16] = g16 ? acc1 : acc0;
                         uint32_t o[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -445,7 +450,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             const uint4 t4 = *reinterpret_cast<const uint4*>(T + tile_off(r, (c0 >> 3) + c16));
                             rs[c16 * 4] = t4.x; rs[c16 * 4 + 1] = t4.y; rs[c16 * 4 + 2] = t4.z; rs[c16 * 4 + 3] = t4.w;
                         }
-                        // pass A (fp32): v = residual + acc + b13, partial row statistics; v is parked as fp16 in the tile
+                        // pass A: v = residual + (acc + b13) in packed half (v is parked as fp16 in the tile anyway), row statistics of
+                        // the parked values accumulated in fp32
+                        uint32_t b3r[16];
+                        ldg256(p.b3h + c0, *reinterpret_cast<uint32_t(*)[8]>(&b3r[0]));
+                        ldg256(p.b3h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&b3r[8]));
                         float sum = 0.f, sq = 0.f;
 #pragma unroll
                         for (int g16 = 0; g16 < 2; ++g16) {
@@ -454,12 +463,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             uint32_t o[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                const float2 rr = h2_to_f2(rs[g16 * 8 + e]);
-                                const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b3 + c0 + g16 * 16 + e * 2));
-                                const float v0 = rr.x + (acc[e * 2] + bb.x), v1 = rr.y + (acc[e * 2 + 1] + bb.y);
-                                sum += v0 + v1;
-                                sq = fmaf(v0, v0, fmaf(v1, v1, sq));
-                                o[e] = pack_sat(v0, v1);
+                                const __half2 v = __hadd2(as_h2(rs[g16 * 8 + e]), __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(b3r[g16 * 8 + e])));
+                                const float2 vf = __half22float2(v);
+                                sum += vf.x + vf.y;
+                                sq = fmaf(vf.x, vf.x, fmaf(vf.y, vf.y, sq));
+                                o[e] = as_u32(v);
                             }
                             st16(T, g16, o);
                         }
@@ -563,7 +571,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
         const EncLayerW& e = m.enc[layer];
         tp.P16 = p.P16[1]; tp.n_w = 3;
         tp.w_row[0] = row_of(e.W11b_h); tp.w_row[1] = row_of(e.W12_h); tp.w_row[2] = row_of(e.W13_h);
-        tp.b2h = e.b12_16; tp.b3 = e.b13;
+        tp.b2h = e.b12_16; tp.b3h = e.b13_16;
         const size_t row0 = (size_t)(mod_base - p.mod) / CB2_MOD_TOTAL;      // row of the current step (sampling) or of member 0 (forward)
         tp.mod16 = p.mod16 + row0 * 768 + layer * 256;
         tp.mod16_stride = mod_stride_b ? 768 : 0;

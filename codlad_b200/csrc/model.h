@@ -20,7 +20,7 @@ struct EncLayerW {
     const float *Win_t, *bin, *Wout_t, *bout;
     const __half *W1b_h, *W2_h, *W11b_h, *W12_h, *W13_h;
     const __half *W1a_h, *W1c_h, *W11a_h, *W11c_h, *W3_h, *Win_h /* 4 blocks */, *Wout_h /* 4 blocks */;
-    const __half *b2_16, *b12_16;      // fp16 copies of the second-layer biases (tensor-core epilogues)
+    const __half *b2_16, *b12_16, *b13_16;      // fp16 copies of the biases the tensor-core epilogues add
 };
 
 struct DecLayerW {

@@ -24,7 +24,7 @@ a.record(); pl.run_edge_kernel(mode, 1); b.record(); torch.cuda.synchronize()
 print("kernel us", a.elapsed_time(b) * 1e3)
 tr = pl.buffer("tc_trace").cpu().tolist()
 n = tr[0]
-names = ["E1 begin", "E1 acc ready", "E1 math done", "E1 handed off", "E2 begin", "E2 acc ready", "E2 math done", "E2 handed off", "E3 begin", "E3 done"]
+names = ["E1 begin", "E1 acc ready", "E1 math done", "E1 handed off", "E2 begin", "E2 acc ready", "E2 math done", "E2 handed off", "drain begin", "drain acc ready", "drain done"]
 t0 = None
 prev = None
 for v in tr[1:1 + n]:
