@@ -692,8 +692,8 @@ int cb2_plan_buffer(cb2_plan* h, const char* name, void* dst, long long dst_byte
     else if (n == "S") { *ptr = p.S; *bytes = N * 128 * 4; }
     else if (n == "out6") { *ptr = p.out6; *bytes = N * 6 * 4; }
     else if (n == "tc_trace") {
-        if (!p.tc_trace) { unsigned long long* t = nullptr; if (dev_alloc(p.allocs, &t, 1024)) return 1; cudaMemsetAsync(t, 0, 8192, (cudaStream_t)stream); p.tc_trace = t; }
-        *ptr = p.tc_trace; *bytes = 8192;
+        if (!p.tc_trace) { unsigned long long* t = nullptr; if (dev_alloc(p.allocs, &t, 6144)) return 1; cudaMemsetAsync(t, 0, 49152, (cudaStream_t)stream); p.tc_trace = t; }
+        *ptr = p.tc_trace; *bytes = 49152;
     }
     else if (n == "mod") { *ptr = p.mod; *bytes = (size_t)p.mod_capacity * CB2_MOD_TOTAL * 4; }
     else { set_error("plan_buffer: unknown buffer '%s'", name); return 1; }

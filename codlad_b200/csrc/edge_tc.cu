@@ -56,6 +56,7 @@ struct TcParams {
     const int *lengths, *frame_of, *nbr_idx;
     float* S;                        // [N, 128] neighbour sums (ENC_NODE / DEC)
     unsigned long long* trace;       // debug: stage timestamps of CTA 0 (nullptr = off)
+    int trace_slot;                  // debug: launch window slot (trace_window)
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 29);
 
     const int tid = threadIdx.x;
+    if (tid == 0) trace_window(p.trace, p.trace_slot, false);
     const int K = p.K, NPT = p.NPT;
     if ((smem_u32(smem) & 1023u) != 0) __trap();                                   // SWIZZLE_128B atoms repeat every 1 KiB
     pdl_launch_dependents();               // the next kernel of the step may start its prologue on SMs this grid leaves idle
@@ -132,7 +134,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
-    const int tile_stride = gridDim.x * 4;
+    // contiguous, balanced tile range of this CTA (sizes differ by at most one tile), processed NSLOT tiles per round
+    const int tile_begin = (int)((long long)blockIdx.x * p.n_tiles / gridDim.x);
+    const int tile_end = (int)((long long)(blockIdx.x + 1) * p.n_tiles / gridDim.x);
+    constexpr int tile_stride = 4;
     constexpr uint32_t IDESC_MAIN = umma_idesc(128, 128, 0, 0);
     constexpr uint32_t IDESC_RED = umma_idesc(128, 16, 1, 0);
 
@@ -172,17 +177,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             };
             pdl_wait();                                               // h_E is produced by the previous kernels of the step
             for (int g = 0; g < 4; ++g)
-                if (blockIdx.x * 4 + g < p.n_tiles) issue_load(g, blockIdx.x * 4 + g);
+                if (tile_begin + g < tile_end) issue_load(g, tile_begin + g);
             uint32_t ph_go = 0;
-            for (int t0 = blockIdx.x * 4; t0 < p.n_tiles; t0 += tile_stride) {
+            for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride) {
                 if (MODE == EDGE_ENC_EDGE) {
                     // residual of the edge update: once MMA 3 has consumed the activation tile, the tile's original h_E rows are
                     // loaded into it again, so E3 reads its residual from shared memory instead of waiting on L2
-                    for (int g = 0; g < 4 && t0 + g < p.n_tiles; ++g) { mbar_wait(bar_m3(g), ph_go); issue_rows(g, bar_res(g)); }
+                    for (int g = 0; g < 4 && t0 + g < tile_end; ++g) { mbar_wait(bar_m3(g), ph_go); issue_rows(g, bar_res(g)); }
                 }
                 for (int g = 0; g < 4; ++g) {
                     const int t = t0 + g;
-                    if (t >= p.n_tiles) break;
+                    if (t >= tile_end) break;
                     mbar_wait(bar_go(g), ph_go);                      // reduction MMA complete (ENC_NODE / DEC) or E3 done (ENC_EDGE)
                     if (MODE == EDGE_ENC_EDGE) {
                         for (int q = 0; q < nv[g]; ++q)
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                                 tma_store_2d(&maps.state, h * 64, out_row0[g] + q * K, T_u32(g) + h * HALF_BYTES + q * K * 128);
                         tma_store_commit();
                     }
-                    if (t + tile_stride < p.n_tiles) {
+                    if (t + tile_stride < tile_end) {
                         if (MODE == EDGE_ENC_EDGE) tma_store_wait_read();        // the store has finished reading the tile
                         issue_load(g, t + tile_stride);
                     }
@@ -224,9 +229,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             };
             mbar_wait(smem_u32(&sBar[0]), 0);                         // weights resident
             uint32_t round = 0;
-            for (int t0 = blockIdx.x * 4; t0 < p.n_tiles; t0 += tile_stride, ++round) {
-                const int n = min(4, p.n_tiles - t0);                  // live slots of this round
-                const int n_next = max(0, min(4, p.n_tiles - (t0 + tile_stride)));
+            for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride, ++round) {
+                const int n = min(4, tile_end - t0);                   // live slots of this round
+                const int n_next = max(0, min(4, tile_end - (t0 + tile_stride)));
                 if (round == 0)
                     for (int g = 0; g < n; ++g) { mbar_wait(bar_load(g), 0); issue_mma(g, 0); }                // TMA landed -> MMA 1
                 for (int g = 0; g < n; ++g) { mbar_wait(bar_epi(g), ph_epi); issue_mma(g, 1); }                // E1 done -> MMA 2
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         const int step_b = tile_stride / p.tiles_per_member, step_t = tile_stride - step_b * p.tiles_per_member;
         auto make_meta = [&](int tile, int b, int tin) {
             TileMeta m{((uint32_t)b << 16) | (uint32_t)tin, 0x80000000u};
-            if (tile >= p.n_tiles) { m.a = 0u; return m; }              // past the end: keep every derived address in bounds
+            if (tile >= tile_end) { m.a = 0u; return m; }              // past the end: keep every derived address in bounds
             const int i0 = tin * NPT;
             const int f = p.single_frame ? 0 : __ldg(p.frame_of + b);    // (dependent load only for multi-frame plans)
             if (q_of_r < min(NPT, p.L - i0))
@@ -323,8 +328,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 trace[0] = (unsigned long long)(++n_trace);
             }
         };
-        TileMeta m0 = first_meta(blockIdx.x * NSLOT + 0), m1 = first_meta(blockIdx.x * NSLOT + 1),
-                 m2 = first_meta(blockIdx.x * NSLOT + 2), m3 = first_meta(blockIdx.x * NSLOT + 3);
+        TileMeta m0 = first_meta(tile_begin + 0), m1 = first_meta(tile_begin + 1), m2 = first_meta(tile_begin + 2), m3 = first_meta(tile_begin + 3);
         auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
         uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
@@ -357,8 +361,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         };
         bool pending3 = false;                                           // slot 3 of the previous round still has to be drained
 
-        for (int t0 = blockIdx.x * NSLOT; t0 < p.n_tiles; t0 += tile_stride) {
-            const int n = min(NSLOT, p.n_tiles - t0);                   // live slots of this round
+        for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride) {
+            const int n = min(NSLOT, tile_end - t0);                    // live slots of this round
             // ================= E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile
             auto epi1 = [&](int s, const uint32_t (&pc)[16]) {
                 unsigned char* T = sT + s * TILE_BYTES;
@@ -510,10 +514,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             ld_pc(m0, pcA);                                             // first E1 of the next round
             prefetch_pa(m0);
         }
-        if (MODE != EDGE_ENC_EDGE && pending3) drain(3, p.n_tiles);        // (ph ^ 1 inside drain = the last round's third parity)
+        if (MODE != EDGE_ENC_EDGE && pending3) drain(3, tile_end);        // (ph ^ 1 inside drain = the last round's third parity)
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) trace_window(p.trace, p.trace_slot, true);
     if (tid >= EPI_THREADS && tid < EPI_THREADS + 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -558,7 +563,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     tp.tiles_per_member = (p.L + tp.NPT - 1) / tp.NPT;
     tp.n_tiles = tp.tiles_per_member * p.NB;
     tp.lengths = p.lengths; tp.frame_of = p.frame_of; tp.nbr_idx = p.nbr_idx; tp.S = p.S;
-    tp.trace = p.tc_trace;
+    tp.trace = p.tc_trace; tp.trace_slot = p.launches & 2047;
     const bool first = (layer == 0 && mode != EDGE_DEC);
     tp.in_is_frame = first ? 1 : 0;
     tp.single_frame = p.F == 1 ? 1 : 0;
@@ -581,7 +586,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
         tp.P16 = p.P16[0]; tp.n_w = 2;
         tp.w_row[0] = row_of(d.W1b2_h); tp.w_row[1] = row_of(d.W2_h); tp.b2h = d.b2_16;
     }
-    const int grid = min(p.num_sms, (tp.n_tiles + 3) / 4);
+    const int grid = min(p.num_sms, tp.n_tiles);
     if (mode == EDGE_ENC_NODE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_NODE>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
     else if (mode == EDGE_ENC_EDGE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_EDGE>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
     else CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_DEC>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));

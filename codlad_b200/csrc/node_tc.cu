@@ -51,6 +51,7 @@ struct NodeTcParams {
     const float *x_t, *noise, *coef;
     float* x_next;
     unsigned long long* trace;   // debug timeline of CTA 0 (nullptr = off)
+    int trace_slot;              // debug: launch window slot (trace_window)
 };
 
 __device__ __forceinline__ void ldg_f32x8(const float* p, float* v) {
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) trace_window(p.trace, p.trace_slot, false);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     pdl_launch_dependents();               // the next kernel of the step may start its prologue on the SMs this grid leaves idle
     const uint32_t bar_full = smem_u32(&sBar[0]), bar_mma = smem_u32(&sBar[1]), bar_act = smem_u32(&sBar[2]);
@@ -425,6 +427,7 @@ __global__ void __launch_bounds__(NODE_EPI_THREADS + 32, 1) node_tc_kernel(const
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) trace_window(p.trace, p.trace_slot, true);
     if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -445,7 +448,7 @@ void base_params(Plan& p, NodeTcParams& np) {
     np.N = p.NB * p.L; np.L = p.L; np.K = p.K;
     np.lengths = p.lengths; np.frame_of = p.frame_of; np.nbr_idx = p.nbr_idx; np.cg_z = p.cg_z;
     np.hV = p.hV; np.hVenc = p.hVenc; np.S = p.S;
-    np.trace = p.tc_trace;
+    np.trace = p.tc_trace; np.trace_slot = p.launches & 2047;
 }
 
 }  // namespace

@@ -239,4 +239,14 @@ inline int get_encode_fn(EncodeTiledFn* out) {
 }
 
 }  // namespace tc
+
+// debug: residency window of one launch (earliest CTA start / latest CTA end, %globaltimer ns) in the plan's "tc_trace" buffer:
+// entry 1024 + 2 slot holds max(~start), entry 1025 + 2 slot max(end); zero-initialised
+__device__ __forceinline__ void trace_window(unsigned long long* trace, int slot, bool end) {
+    if (trace == nullptr) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(trace + 1024 + 2 * slot + (end ? 1 : 0), end ? t : ~t);
+}
+
 }  // namespace cb2

@@ -176,7 +176,7 @@ class Plan:
             "E": (torch.float32, (self.F, self.L, self.K, 128)), "hE0": (edge_dtype, (self.F, self.L, self.K, 128)),
             "hE": (edge_dtype, (self.NB, self.L, self.K, 128)), "hV": (torch.float32, (self.NB, self.L, 128)),
             "S": (torch.float32, (self.NB, self.L, 128)), "out6": (torch.float32, (self.NB, self.L, 6)),
-            "tc_trace": (torch.int64, (1024,)),
+            "tc_trace": (torch.int64, (6144,)),
         }[name]
         out = torch.empty(spec[1], device=self.device, dtype=spec[0])
         N.check(N.lib().cb2_plan_buffer(self.handle, name.encode(), N.dptr(out), out.numel() * out.element_size(), N.stream_ptr()),

@@ -34,3 +34,10 @@ for v in tr[1:1 + n]:
     if t0 is None: t0 = t
     print(f"{(t - t0) / 1000:8.2f} us  (+{0 if prev is None else (t - prev) / 1000:6.2f})  slot {s}  {names[ev]}")
     prev = t
+import numpy as np
+w = np.array(tr[600:600 + 2 * 148], dtype=np.int64).reshape(-1, 2)
+st, en = w[:, 0], w[:, 1]
+print("CTA start spread us", (st.max() - st.min()) / 1e3, " first start -> last end us", (en.max() - st.min()) / 1e3)
+d = (en - st) / 1e3
+print("CTA durations us: min %.1f mean %.1f max %.1f" % (d.min(), d.mean(), d.max()))
+print("end times rel. first start, sorted:", np.sort((en - st.min()) / 1e3).round(1).tolist()[::8])
