@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     constexpr uint32_t IDESC_RED = umma_idesc(128, 16, 1, 0);
 
     if (tid >= EPI_THREADS) {
-        // =========================================================================== control warps (one lane each)
+        // =========================================================================== control warps
         // warp 16 issues every MMA, warp 17 every TMA, in the order the epilogue warps consume them: the epilogue
         // threads never execute issue code and a tile's MMA / TMA latency is covered by the other tiles' epilogues.
         // (MMA and TMA issue are split because a thread's tcgen05.mma stalls behind its own in-flight bulk copies.)
+        // Both warps run their control flow with all 32 lanes and issue through elect.sync (see elect_one()).
         auto T_u32 = [&](int g) { return smem_u32(sT + g * TILE_BYTES); };
         auto bar_load = [&](int g) { return smem_u32(&sBar[1 + 3 * g]); };
         auto bar_acc = [&](int g) { return smem_u32(&sBar[2 + 3 * g]); };
@@ -153,19 +154,25 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         auto bar_go = [&](int g) { return smem_u32(&sBar[13 + g]); };          // slot g's operand tile may be recycled
         auto bar_m3 = [&](int g) { return smem_u32(&sBar[17 + g]); };          // ENC_EDGE: MMA 3 complete
         auto bar_res = [&](int g) { return smem_u32(&sBar[21 + g]); };         // ENC_EDGE: residual rows re-loaded into the tile
-        if (tid == EPI_THREADS + 32) {
-            // ------------------------------------------------------------------ TMA thread
+        if (tid >= EPI_THREADS + 32) {
+            // ------------------------------------------------------------------ TMA warp
             const CUtensorMap* in_map = p.in_is_frame ? &maps.in_frame : &maps.state;
-            mbar_expect_tx(smem_u32(&sBar[0]), (uint32_t)(N_W * TILE_BYTES));
-            for (int m = 0; m < N_W; ++m)
-                for (int h = 0; h < 2; ++h)
-                    tma_load_2d(smem_u32(sW + m * TILE_BYTES + h * HALF_BYTES), &maps.weights, h * 64, p.w_row[m], smem_u32(&sBar[0]));
+            if (elect_one()) {
+                mbar_expect_tx(smem_u32(&sBar[0]), (uint32_t)(N_W * TILE_BYTES));
+                for (int m = 0; m < N_W; ++m)
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d(smem_u32(sW + m * TILE_BYTES + h * HALF_BYTES), &maps.weights, h * 64, p.w_row[m], smem_u32(&sBar[0]));
+            }
+            __syncwarp();
             int nv[4], out_row0[4], in_row0[4];
             auto issue_rows = [&](int g, uint32_t bar) {              // TMA of the tile's h_E rows, one box per node and half
-                mbar_expect_tx(bar, (uint32_t)(nv[g] * K * 256));
-                for (int q = 0; q < nv[g]; ++q)
-                    for (int h = 0; h < 2; ++h)
-                        tma_load_2d(T_u32(g) + h * HALF_BYTES + q * K * 128, in_map, h * 64, in_row0[g] + q * K, bar);
+                if (elect_one()) {
+                    mbar_expect_tx(bar, (uint32_t)(nv[g] * K * 256));
+                    for (int q = 0; q < nv[g]; ++q)
+                        for (int h = 0; h < 2; ++h)
+                            tma_load_2d(T_u32(g) + h * HALF_BYTES + q * K * 128, in_map, h * 64, in_row0[g] + q * K, bar);
+                }
+                __syncwarp();
             };
             auto issue_load = [&](int g, int t) {
                 const int b = t / p.tiles_per_member;
@@ -189,43 +196,53 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     const int t = t0 + g;
                     if (t >= tile_end) break;
                     mbar_wait(bar_go(g), ph_go);                      // reduction MMA complete (ENC_NODE / DEC) or E3 done (ENC_EDGE)
+                    // (bulk-copy groups belong to the issuing thread: elect.sync picks the same lane every time)
                     if (MODE == EDGE_ENC_EDGE) {
-                        for (int q = 0; q < nv[g]; ++q)
-                            for (int h = 0; h < 2; ++h)
-                                tma_store_2d(&maps.state, h * 64, out_row0[g] + q * K, T_u32(g) + h * HALF_BYTES + q * K * 128);
-                        tma_store_commit();
+                        if (elect_one()) {
+                            for (int q = 0; q < nv[g]; ++q)
+                                for (int h = 0; h < 2; ++h)
+                                    tma_store_2d(&maps.state, h * 64, out_row0[g] + q * K, T_u32(g) + h * HALF_BYTES + q * K * 128);
+                            tma_store_commit();
+                        }
+                        __syncwarp();
                     }
                     if (t + tile_stride < tile_end) {
-                        if (MODE == EDGE_ENC_EDGE) tma_store_wait_read();        // the store has finished reading the tile
+                        if (MODE == EDGE_ENC_EDGE) { if (elect_one()) tma_store_wait_read(); __syncwarp(); }   // the store has finished reading the tile
                         issue_load(g, t + tile_stride);
                     }
                 }
                 ph_go ^= 1;
             }
-            if (MODE == EDGE_ENC_EDGE) tma_store_wait_all();
-        } else if (tid == EPI_THREADS) {
-            // ------------------------------------------------------------------ MMA thread
+            if (MODE == EDGE_ENC_EDGE) { if (elect_one()) tma_store_wait_all(); __syncwarp(); }
+        } else {
+            // ------------------------------------------------------------------ MMA warp
             uint32_t ph_epi = 0;
             auto issue_mma = [&](int g, int w_slot) {                 // 128x128x128 GEMM, A = tile g, B = weight slot
                 tc_fence_after();
+                // descriptors of k-step 0; a k-step advances only the (16-byte granular) start-address field
+                const uint64_t a0 = umma_desc(T_u32(g), 16, 1024), b0 = umma_desc(smem_u32(sW + w_slot * TILE_BYTES), 16, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-                    umma_f16(tmem_base + (uint32_t)(g * 128), umma_desc(T_u32(g) + koff, 16, 1024),
-                             umma_desc(smem_u32(sW + w_slot * TILE_BYTES) + koff, 16, 1024), IDESC_MAIN, k > 0);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t koff = (uint64_t)(((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4);
+                        umma_f16(tmem_base + (uint32_t)(g * 128), a0 + koff, b0 + koff, IDESC_MAIN, k > 0);
+                    }
+                    umma_commit(bar_acc(g));
                 }
-                umma_commit(bar_acc(g));
+                __syncwarp();
             };
             auto issue_reduce = [&](int g) {                          // D[c, q] = sum_r G[r, c] Ind[q, r]
                 tc_fence_after();
+                const uint64_t a0 = umma_desc(T_u32(g), HALF_BYTES, 1024), b0 = umma_desc(smem_u32(sInd), 16, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t a = umma_desc(T_u32(g) + (uint32_t)(k * 16 * 128), HALF_BYTES, 1024);   // A = G^T: MN-major view, 16 rows (K) per step
-                    const uint64_t bd = umma_desc(smem_u32(sInd) + (uint32_t)((k >> 2) * (16 * 128) + (k & 3) * 32), 16, 1024);
-                    umma_f16(tmem_base + (uint32_t)(g * 128), a, bd, IDESC_RED, k > 0);
+                    for (int k = 0; k < 8; ++k)                        // A = G^T: MN-major view, 16 rows (K) per step
+                        umma_f16(tmem_base + (uint32_t)(g * 128), a0 + (uint64_t)((k * 16 * 128) >> 4),
+                                 b0 + (uint64_t)(((k >> 2) * (16 * 128) + (k & 3) * 32) >> 4), IDESC_RED, k > 0);
+                    umma_commit(bar_acc(g));
+                    umma_commit(bar_go(g));                            // ... and the operand tile is free once these MMAs complete
                 }
-                umma_commit(bar_acc(g));
-                umma_commit(bar_go(g));                                // ... and the operand tile is free once these MMAs complete
+                __syncwarp();
             };
             mbar_wait(smem_u32(&sBar[0]), 0);                         // weights resident
             uint32_t round = 0;
@@ -238,7 +255,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 ph_epi ^= 1;
                 for (int g = 0; g < n; ++g) {                                                                  // E2 done -> reduction MMA / MMA 3
                     mbar_wait(bar_epi(g), ph_epi);
-                    if (MODE == EDGE_ENC_EDGE) { issue_mma(g, 2); umma_commit(bar_m3(g)); } else issue_reduce(g);
+                    if (MODE == EDGE_ENC_EDGE) { issue_mma(g, 2); if (elect_one()) umma_commit(bar_m3(g)); __syncwarp(); } else issue_reduce(g);
                 }
                 ph_epi ^= 1;
                 // E3 done: the accumulator is drained -> MMA 1 of the slot's next tile as soon as its TMA has landed.
@@ -247,7 +264,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 for (int g = 0; g < n; ++g) {
                     if (MODE == EDGE_ENC_EDGE) {
                         mbar_wait(bar_epi(g), ph_epi);
-                        mbar_arrive(bar_go(g));                                                                // tile complete in smem: store + recycle
+                        if (elect_one()) mbar_arrive(bar_go(g));                                               // tile complete in smem: store + recycle
+                        __syncwarp();
                     } else {
                         mbar_wait(smem_u32(&sBar[25 + g]), round & 1);                                         // reduced sums read out of TMEM
                     }

@@ -65,6 +65,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a fully converged warp.  The single-thread instructions (tcgen05.mma / commit, TMA) take their operands from
+// uniform registers; issued under elect.sync from warp-uniform control flow they compile to straight-line code, whereas a
+// `lane == 0` branch makes the compiler wrap each of them in a per-lane serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
