@@ -352,7 +352,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
         uint32_t pcA[16], pcB[16];                                      // gathered halves, double buffered one stage ahead
         pdl_wait();                                                     // P16 / S / h_E belong to the previous kernels of the step
-        ld_pc(m0, pcA);
 
         // ENC_NODE / DEC: "E3" (read the reduced sums out of TMEM, store S, release the accumulator, fetch the slot's next
         // metadata) is not a stage of its own: it rides at the tail of the FOLLOWING stage, when the (short) reduction MMA
@@ -381,6 +380,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 
         for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride) {
             const int n = min(NSLOT, tile_end - t0);                    // live slots of this round
+            // gathered halves of the round's first tile: issued here, not at the bottom of the previous round, so that the
+            // compiler's scoreboard wait at the loop back-edge does not expose the gather latency (it now hides behind the
+            // first accumulator wait)
+            ld_pc(m0, pcA);
+            prefetch_pa(m0);
             // ================= E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile
             auto epi1 = [&](int s, const uint32_t (&pc)[16]) {
                 unsigned char* T = sT + s * TILE_BYTES;
@@ -529,8 +533,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             }
             ph ^= 1;
             ph_res ^= 1;
-            ld_pc(m0, pcA);                                             // first E1 of the next round
-            prefetch_pa(m0);
         }
         if (MODE != EDGE_ENC_EDGE && pending3) drain(3, tile_end);        // (ph ^ 1 inside drain = the last round's third parity)
     }

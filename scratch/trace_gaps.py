@@ -36,3 +36,6 @@ dur = (en - st) / 1e3
 print("launch windows:", len(st), " span us", (en[-1] - t0) / 1e3, " sum of windows us", dur.sum(), " sum of gaps us", gaps.sum())
 for i in range(800, 840):
     print(f"{(st[i] - t0) / 1e3:9.2f} .. {(en[i] - t0) / 1e3:9.2f}   dur {dur[i]:6.2f}   gap before {0 if i == 0 else gaps[i - 1]:6.2f}")
+# per-step summary from end-to-end deltas
+ends = en[800:800 + 17]
+print("end deltas:", np.diff(ends / 1e3).round(1).tolist(), " step us", (en[816] - en[800]) / 1e3)
