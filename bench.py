@@ -34,6 +34,15 @@ METRIC = "backmapped residues/sec (100-step, 10-ensemble)"
 UNIT = "residues/s"
 L_RES, ENSEMBLE, T_STEPS = 300, 10, 100
 WORKLOAD = "configs[1]: PED-like 300-residue IDP, N6, 100-step latent sampling, num_ensemble=10"
+# The bench line is configs[1] (`--workload c2`, the configuration the metric is quoted on).  c3 / c4 are BASELINE.json's larger
+# configurations at their per-GPU shard size, runnable with the same harness for scale checks (not bench lines).
+WORKLOADS = {
+    "c2": dict(desc=WORKLOAD, L=300, frames=1, ensemble=10, k=64, compact=0.0, vae="N6"),
+    "c3": dict(desc="configs[2] per-GPU shard: 32 PDB-like proteins x 500 residues, K3 decoder, 100 steps, num_ensemble=1",
+               L=500, frames=32, ensemble=1, k=64, compact=0.0, vae="K3"),
+    "c4": dict(desc="configs[3]: one Atlas-like 2000-residue frame, K4 decoder, k_neighbors=48, 100 steps, 32 members over the GPUs",
+               L=2000, frames=1, ensemble=32, k=48, compact=0.0, vae="K4"),
+}
 
 # canonical algorithmic work per edge of the three per-edge kernels: GEMM flops only
 EDGE_FLOPS = {0: 2 * 2 * 128 * 128, 1: 2 * 3 * 128 * 128, 2: 2 * 2 * 128 * 128}
@@ -93,13 +102,18 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _workload(rank: int):
-    """Synthetic protein of this rank + pinned host FrameSet (SURVEY.md section 8d generators)."""
+def _workload(rank: int, name: str = "c2", world: int = 1):
+    """Synthetic protein(s) of this rank + host FrameSet (SURVEY.md section 8d generators)."""
     from codlad_b200 import sampler, synthetic
-    prot = synthetic.make_protein(L_RES, 1, seed=1002 + rank)
-    batch = synthetic.collate(prot)
-    fs = sampler.frames_from_batch(batch, prot.info, ENSEMBLE)
-    return prot, batch, fs
+    w = WORKLOADS[name]
+    if w["frames"] == 1:
+        prot = synthetic.make_protein(w["L"], 1, seed=1002 + (rank if name == "c2" else 0), compact=w["compact"])
+        batch = synthetic.collate(prot)
+        ens = w["ensemble"] if name == "c2" else max(1, w["ensemble"] // world)      # c4 shards its members over the ranks
+        return prot, batch, sampler.frames_from_batch(batch, prot.info, ens)
+    prots = [synthetic.make_protein(w["L"], 1, seed=3000 + rank * w["frames"] + i, compact=w["compact"]) for i in range(w["frames"])]
+    batch = synthetic.collate_many(prots)
+    return prots[0], batch, sampler.frames_from_batch(batch, [p.info for p in prots], w["ensemble"])
 
 
 # ------------------------------------------------------------------------------------------------ CPU port timing
@@ -182,6 +196,7 @@ def main():
     ap.add_argument("--impl", default="codlad_b200", choices=["codlad_b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CB2_PRECISION", "f16"), choices=["f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the bench line; c3 / c4 = scale checks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -199,10 +214,12 @@ def main():
     from codlad_b200 import sampler, weights
 
     dev = torch.device("cuda", local)
-    prot, batch, fs = _workload(rank)
+    wl = WORKLOADS[args.workload]
+    prot, batch, fs = _workload(rank, args.workload, world)
     fs.pin()
-    bm = sampler.Backmapper(weights.init_denoiser_state(0), weights.init_vae_decode_state(0), "N6", num_sampling_steps=T_STEPS,
-                            precision=args.precision)
+    angle = wl["vae"] in ("K3", "K4")
+    bm = sampler.Backmapper(weights.init_denoiser_state(0), weights.init_vae_decode_state(0, angle, (wl["vae"], sampler.VAE_DATA[wl["vae"]])),
+                            wl["vae"], k_neighbors=wl["k"], num_sampling_steps=T_STEPS, precision=args.precision)
     plan = bm.upload(fs)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -234,7 +251,7 @@ def main():
     barrier()
     launches = plan.launches - l0
     ms_dev = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / args.steps)
-    residues = L_RES * ENSEMBLE * world
+    residues = fs.NB * fs.L * world
     value = residues / (ms_dev * 1e-3)
 
     # ---- end to end through the host API: pinned host inputs -> H2D -> whole path -> D2H coordinates
@@ -280,7 +297,7 @@ def main():
                 "flops_per_launch": EDGE_FLOPS[mode] * edges, "algorithmic_bytes_per_launch": edges * 128 * 2 * (2 if args.precision == "f16" else 4)}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and args.workload == "c2":
         cpu = cpu_port_sample(denoiser_steps=2)
 
     if rank == 0:
@@ -288,9 +305,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (tcgen05, fp32 accumulate)" if args.precision == "f16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "residues_per_step_per_gpu": L_RES * ENSEMBLE, "diffusion_steps": T_STEPS, "k_neighbors": plan.K,
+            "config": {"workload": wl["desc"], "residues_per_step_per_gpu": fs.NB * fs.L, "diffusion_steps": T_STEPS, "k_neighbors": plan.K,
                        "weights": "random init (seed 0), adaLN layers re-randomised", "l2": "flushed between timed steps (512 MiB fill)",
-                       "sharding": "one protein x 10 members per GPU, no collective"},
+                       "sharding": f"{fs.F} frame(s) x {fs.NB // fs.F} member(s) per GPU, no collective"},
             "e2e": {"value": residues / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))

@@ -571,7 +571,19 @@ static int enqueue_loop(cb2_plan* h, float* x, const float* noise, cudaStream_t 
     float *cur = h->xa, *nxt = h->xb;
     for (int step = p.coef_steps - 1; step >= 0; --step) {
         const float* mod_row = p.mod + (size_t)step * CB2_MOD_TOTAL;     // every member shares the step -> stride 0
-        if (int e = run_forward(p, cur, mod_row, 0, noise + (size_t)step * n3, nxt, p.coef + (size_t)step * 8, s)) return e;
+        if (int e = run_forward(p, cur, mod_row, 0, noise + (size_t)step * n3, nxt, p.coef + (size_t)step * 8, s)) {
+            char prev[900];
+            snprintf(prev, sizeof(prev), "%s", g_err);
+            const unsigned int* tl = edge_tc_trap_log();
+            if (tl != nullptr) {
+                char w[600]; int n = 0;
+                for (int i = 0; i < 18 && n < 560; ++i)
+                    if (tl[4 + 2 * i]) n += snprintf(w + n, sizeof(w) - n, " w%d:bar+0x%x/p%u", i, tl[4 + 2 * i] & 0xfffu, tl[5 + 2 * i] >> 16);
+                set_error("%s [sampling step %d; block %u timed-out waits:%s]", prev, step, tl[0] - 1u, w);
+            }
+            else set_error("%s [sampling step %d]", prev, step);
+            return e;
+        }
         float* t = cur; cur = nxt; nxt = t;
     }
     CB2_CUDA(cudaMemcpyAsync(x, cur, n3 * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -23,6 +23,7 @@
 //   * epilogue arithmetic is packed fp16 (HFMA2); GELU uses tanh.approx (one MUFU per element) on a refitted 2-term
 //     inner polynomial: |err| < 2.8e-4 abs against erf-GELU before the MUFU's own 2^-11 relative error -- the same
 //     order as the fp16 rounding of the activation it feeds.  (The fp32 tier uses erff.)
+#include <cstring>
 #include "model.h"
 #include "tc_common.cuh"
 
@@ -393,6 +394,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
                 ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
                 mark(0, s);
+                // The warps that do not drain (cq != 0) never wait for the slot's third commit (the reduction MMA), and the phases
+                // on either side of it have the same parity: a warp that ran a whole E2 phase ahead of a straggler would sail
+                // through the accumulator wait below on the stale "MMA 2 complete" state (seen as a rare dead-lock on large
+                // working sets, where TLB misses skew the warps).  The slot's "drained" barrier advances once per round and
+                // only after the reduction has completed, so it orders them exactly.
+                if (MODE != EDGE_ENC_EDGE && cq != 0 && t0 != tile_begin) mbar_wait(smem_u32(&sBar[25 + s]), ph ^ 1);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                 tc_fence_after();
                 mark(1, s);
@@ -549,6 +556,10 @@ size_t tc_smem_bytes(int mode) {
 
 }  // namespace
 
+unsigned int* g_trap_host = nullptr;       // CB2_TRAP_DEBUG: host view of the time-out record of this file's kernels
+
+const unsigned int* edge_tc_trap_log() { return g_trap_host; }
+
 int edge_tc_prepare(Plan& p) {
     if (p.K > 128 || p.K < 1) { set_error("edge_tc: K=%d unsupported", p.K); return 1; }
     EncodeTiledFn fn = nullptr;
@@ -558,6 +569,13 @@ int edge_tc_prepare(Plan& p) {
     if (encode_rows_map(fn, &m->in_frame, p.hE0, (size_t)p.F * p.L * p.K, p.K)) return 1;
     if (encode_rows_map(fn, &m->state, p.hE, (size_t)p.NB * p.L * p.K, p.K)) return 1;
     if (encode_rows_map(fn, &m->weights, p.model->dev_f16, (size_t)p.model->n_f16_blocks * 128, 128)) return 1;
+    if (getenv("CB2_TRAP_DEBUG") != nullptr && g_trap_host == nullptr) {
+        unsigned int* dptr = nullptr;
+        CB2_CUDA(cudaHostAlloc(&g_trap_host, 256, cudaHostAllocMapped));
+        memset(g_trap_host, 0, 256);
+        CB2_CUDA(cudaHostGetDevicePointer(&dptr, g_trap_host, 0));
+        CB2_CUDA(cudaMemcpyToSymbol(tc::g_trap_log, &dptr, sizeof(dptr)));
+    }
     int dev = 0;
     CB2_CUDA(cudaGetDevice(&dev));
     CB2_CUDA(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, dev));

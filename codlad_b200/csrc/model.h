@@ -116,6 +116,7 @@ int launch_node_init_tc(Plan& p, const float* x, cudaStream_t s);
 int launch_node_update_tc(Plan& p, int phase, const float* mod_base, int mod_stride_b, const float* x_t, const float* noise,
                           float* x_next, const float* coef_row, cudaStream_t s);
 void edge_tc_release(Plan& p);
+const unsigned int* edge_tc_trap_log();      // debug (CB2_TRAP_DEBUG): record of a timed-out barrier wait, or nullptr
 
 enum EdgeMode { EDGE_ENC_NODE = 0, EDGE_ENC_EDGE = 1, EDGE_DEC = 2 };
 

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -14,7 +15,7 @@ namespace tc {
 
 constexpr int TILE_BYTES = 128 * 128 * 2;      // one 128x128 fp16 operand tile (two 64-column SW128 halves)
 constexpr int HALF_BYTES = TILE_BYTES / 2;
-constexpr uint32_t SPIN_LIMIT = 1u << 26;      // mbarrier waits trap instead of hanging the GPU
+constexpr uint32_t SPIN_LIMIT = 1u << 22;      // mbarrier waits trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -23,6 +24,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// debug (CB2_TRAP_DEBUG=1): host-mapped words that receive (barrier address, parity, thread, block) of the wait that timed out
+static __device__ unsigned int* g_trap_log = nullptr;
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, bool final) {
+    if (g_trap_log != nullptr && blockIdx.x == g_trap_log[0] - 1u + (g_trap_log[0] == 0u ? blockIdx.x + 1u : 0u)) {
+        // first block to time out claims the log; every stuck warp of that block records its wait in its own slot
+        const unsigned int claimed = atomicCAS(g_trap_log, 0u, blockIdx.x + 1u);
+        if (claimed == 0u || claimed == blockIdx.x + 1u) {
+            unsigned int* e = g_trap_log + 4 + (threadIdx.x >> 5) * 2;
+            e[0] = bar; e[1] = (parity << 16) | (threadIdx.x & 0xffffu);
+            __threadfence_system();
+        }
+    }
+    if (final) __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // A waiting warp must not eat the issue slots of the warps doing arithmetic on the same scheduler: back off with
@@ -33,7 +48,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
         __nanosleep(64);
-        if (++spins > SPIN_LIMIT) __trap();
+        if (++spins == SPIN_LIMIT) mbar_timeout(bar, parity, false);      // (debug record; keeps waiting so that the other stuck warps record too)
+        if (spins > SPIN_LIMIT + (SPIN_LIMIT >> 1)) mbar_timeout(bar, parity, true);
     }
 }
 // the control warps' variant: no back-off (try_wait suspends in hardware; these warps have nothing else to do and every
@@ -44,7 +60,8 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > SPIN_LIMIT) __trap();
+        if (++spins == SPIN_LIMIT) mbar_timeout(bar, parity, false);      // (debug record; keeps waiting so that the other stuck warps record too)
+        if (spins > SPIN_LIMIT + (SPIN_LIMIT >> 1)) mbar_timeout(bar, parity, true);
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -224,9 +241,10 @@ template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    static const bool no_pdl = getenv("CB2_NO_PDL") != nullptr;      // debug switch: plain stream order
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }

@@ -34,7 +34,7 @@ class DenoiserEngine:
         del keep
 
     def close(self):
-        if getattr(self, "handle", None) and N is not None:
+        if getattr(self, "handle", None) and N is not None and getattr(N, "lib", None) is not None:
             N.lib().cb2_denoiser_destroy(self.handle)
             self.handle = None
 
@@ -62,7 +62,7 @@ class VaeEngine:
         del keep
 
     def close(self):
-        if getattr(self, "handle", None) and N is not None:
+        if getattr(self, "handle", None) and N is not None and getattr(N, "lib", None) is not None:
             N.lib().cb2_vae_destroy(self.handle)
             self.handle = None
 
@@ -85,7 +85,7 @@ class Plan:
         self._lengths = None
 
     def close(self):
-        if getattr(self, "handle", None) and N is not None:
+        if getattr(self, "handle", None) and N is not None and getattr(N, "lib", None) is not None:
             N.lib().cb2_plan_destroy(self.handle)
             self.handle = None
 

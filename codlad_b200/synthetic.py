@@ -100,5 +100,19 @@ def collate(protein: SyntheticProtein, frames=None, prot_idx: int = 0) -> dict:
     }
 
 
+def collate_many(proteins, frame: int = 0) -> dict:
+    """One batch dict over several proteins (one frame each), offsets as CG_collate applies them
+    (utils/dataset_module.py:259-295: neighbour lists shifted by the running residue count)."""
+    parts = [collate(p, [frame], prot_idx=i) for i, p in enumerate(proteins)]
+    out, off = {}, 0
+    nbrs = []
+    for part, p in zip(parts, proteins):
+        nbrs.append(part["CG_nbr_list"] + off)
+        off += p.L
+    for k in parts[0]:
+        out[k] = torch.cat(nbrs, 0) if k == "CG_nbr_list" else torch.cat([part[k] for part in parts], 0)
+    return out
+
+
 def latent_noise(shape, seed: int) -> torch.Tensor:
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))

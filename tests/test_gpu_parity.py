@@ -451,3 +451,36 @@ def test_module_forward_matches_oracle_ragged_batch(R):
     m = c["mask"] & torch.tensor([True, True])[:, None]
     m[1] = False                                       # rows of the shorter protein see topk's arbitrary tie order in the reference
     assert np.abs(out.numpy() - g["out"])[m.numpy()].max() < 5e-5
+
+
+# --------------------------------------------------------------------------------------- BASELINE configs[2] / [3] shapes
+@pytest.mark.parametrize("L,K,frames,ens", [(2000, 48, 1, 4), (500, 64, 6, 1)])
+def test_whole_path_at_large_config_shapes(eng, L, K, frames, ens):
+    """configs[3]-shaped (one 2000-residue frame, k_neighbors=48, K4 decoder) and configs[2]-shaped (several 500-residue
+    proteins, K3 decoder) passes through the f16 tier: many tiles per CTA and a working set beyond L2.  The oracle
+    would need hours here, so the checks are the size-independent ones: the CUDA-graph replay equals the eager loop bit
+    for bit (the step loop has a fixed reduction order), outputs are finite, ensemble members that share a frame and
+    start from the same noise give identical coordinates, and the decoded bond lengths are the residue-type table
+    entries (a property of the IC decoder whatever the latent).  Regression test for the barrier-parity hazard that
+    dead-locked the per-edge kernel on exactly this kind of working set."""
+    from codlad_b200 import sampler
+    vae_type = "K4" if frames == 1 else "K3"
+    prots = [synthetic.make_protein(L, 1, seed=4100 + i) for i in range(frames)]
+    batch = synthetic.collate(prots[0]) if frames == 1 else synthetic.collate_many(prots)
+    fs = sampler.frames_from_batch(batch, [p.info for p in prots], ens)
+    vsd = weights.init_vae_decode_state(0, True, (vae_type, sampler.VAE_DATA[vae_type]))
+    bm = sampler.Backmapper(weights.init_denoiser_state(0), vsd, vae_type, k_neighbors=K, precision="f16")
+    plan = bm.upload(fs)
+    z = synthetic.latent_noise((fs.F, L, 3), 7).repeat(ens, 1, 1)                       # members of a frame share their noise
+    noise = synthetic.latent_noise((bm.T, fs.F, L, 3), 8).repeat(1, ens, 1, 1)
+    eager = {k: v.clone() for k, v in bm.sample(plan, fs, z, noise, use_graph=False).items() if v is not None}
+    graph = bm.sample(plan, fs, z, noise, use_graph=True)
+    for k in ("latent", "xyz", "ic_recon"):
+        assert torch.isfinite(eager[k]).all(), k
+        assert torch.equal(eager[k], graph[k]), f"{k}: graph replay differs from the eager loop"
+    lat = eager["latent"].reshape(ens, fs.F, L, 3)
+    assert torch.equal(lat[0], lat[-1]), "members with identical noise diverged"
+    ic = eager["ic_recon"].reshape(fs.NB, L, 13, 3).cpu()
+    table = vsd["equivaraintconv.backbone_dist.weight"]
+    cg_z = fs.cg_z.long()[fs.frame_of.long()]
+    assert torch.equal(ic[:, :, :3, 0], table[cg_z]), "backbone bond lengths are a table lookup"
