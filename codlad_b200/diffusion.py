@@ -160,6 +160,24 @@ class SpacedDiffusion:
         c = self._coef_on(x.device)[t].view(-1, *([1] * (x.dim() - 1)), 8)
         return {"sample": nxt, "pred_xstart": c[..., 2] * x - c[..., 3] * eps}
 
+    def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, x_self_cond=None):
+        """gaussian_diffusion.py:262-360 for the shipped configuration (epsilon prediction, learned-range variance):
+        dict(mean, variance, log_variance, pred_xstart).  Caller-facing glue for code that inspects one reverse step; the
+        sampling loop itself never materialises these (they are fused into the final node kernel / cb2_p_sample)."""
+        if denoised_fn is not None or clip_denoised:
+            raise NotImplementedError("denoised_fn / clip_denoised are not used by the reference's sampling path")
+        model_kwargs = model_kwargs or {}
+        map_t = torch.tensor(self.timestep_map, device=t.device, dtype=t.dtype)[t]     # respace.py:124-125
+        out = model(x, map_t, **model_kwargs).to(torch.float32)
+        C_ = x.shape[-1]
+        eps, v = out[..., :C_], out[..., C_:]
+        c = self._coef_on(x.device)[t].view(-1, *([1] * (x.dim() - 1)), 8)
+        frac = (v + 1) / 2
+        log_variance = frac * c[..., 1] + (1 - frac) * c[..., 0]
+        pred_xstart = c[..., 2] * x - c[..., 3] * eps
+        mean = c[..., 4] * pred_xstart + c[..., 5] * x
+        return {"mean": mean, "variance": torch.exp(log_variance), "log_variance": log_variance, "pred_xstart": pred_xstart}
+
     def training_losses(self, *a, **k):
         raise NotImplementedError("train_latent step (SURVEY.md section 8, row f-1) is not part of this round")
 

@@ -99,3 +99,25 @@ def test_reference_surface_modules_have_reference_state_dict_keys():
     import torch
     x = torch.randn(2, 5, 3)
     assert torch.allclose(get_norm_feature(get_norm_feature(x, norm_in=False, dataname="Atlas_K4"), norm_in=True, dataname="Atlas_K4"), x, atol=1e-5)
+
+
+def test_p_mean_variance_matches_oracle_update():
+    """p_mean_variance (gaussian_diffusion.py:262-360) against the oracle's one-step update: mean + exp(log_variance / 2) * noise
+    must reproduce oracle.restate.p_sample_update for every respaced step (pure host/torch glue, runs without the CUDA library)."""
+    from codlad_b200.diffusion import create_diffusion
+    from oracle import restate as R
+    diff = create_diffusion("100")
+    sched = R.respaced_schedule(100)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 7, 3, generator=g)
+    out = torch.randn(2, 7, 6, generator=g)
+    noise = torch.randn(2, 7, 3, generator=g)
+    model = lambda x_, t_, **kw: out
+    for step in (0, 1, 50, 99):
+        t = torch.full((2,), step, dtype=torch.long)
+        pmv = diff.p_mean_variance(model, x, t, clip_denoised=False)
+        nz = 0.0 if step == 0 else 1.0
+        got = pmv["mean"] + nz * torch.exp(0.5 * pmv["log_variance"]) * noise
+        ref = R.p_sample_update(x, out, step, noise, sched)
+        assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6), step
+        assert torch.allclose(pmv["variance"], torch.exp(pmv["log_variance"]))
