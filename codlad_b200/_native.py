@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcodlad_b200.so")
+LIB_PATH = os.environ.get("CB2_LIB") or os.path.join(_HERE, "libcodlad_b200.so")      # CB2_LIB: experiment builds
 ABI_VERSION = 1
 
 PRECISION = {"fp32": 0, "f32": 0, "f16": 1, "fp16": 1}

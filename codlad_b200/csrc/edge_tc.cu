@@ -58,6 +58,7 @@ struct TcParams {
     float* S;                        // [N, 128] neighbour sums (ENC_NODE / DEC)
     unsigned long long* trace;       // debug: stage timestamps of CTA 0 (nullptr = off)
     int trace_slot;                  // debug: launch window slot (trace_window)
+    int trace_epi;                   // debug: record the epilogue timeline too (CB2_TRACE_CTRL_ONLY unset)
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -149,6 +150,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         // (MMA and TMA issue are split because a thread's tcgen05.mma stalls behind its own in-flight bulk copies.)
         // Both warps run their control flow with all 32 lanes and issue through elect.sync (see elect_one()).
         auto T_u32 = [&](int g) { return smem_u32(sT + g * TILE_BYTES); };
+        // debug timeline of CTA 0's control warps (lane 0): MMA warp -> trace[5120..], TMA warp -> trace[5632..]
+        unsigned long long* ctr = (p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0) ? p.trace + (tid >= EPI_THREADS + 32 ? 5632 : 5120) : nullptr;
+        int n_ctr = 0;
+        auto cmark = [&](int ev, int g) {
+            if (ctr != nullptr && n_ctr < 500) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                ctr[1 + n_ctr] = (t << 8) | (unsigned long long)((ev << 2) | g);
+                ctr[0] = (unsigned long long)(++n_ctr);
+            }
+        };
         auto bar_load = [&](int g) { return smem_u32(&sBar[1 + 3 * g]); };
         auto bar_acc = [&](int g) { return smem_u32(&sBar[2 + 3 * g]); };
         auto bar_epi = [&](int g) { return smem_u32(&sBar[3 + 3 * g]); };
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     const int t = t0 + g;
                     if (t >= tile_end) break;
                     mbar_wait(bar_go(g), ph_go);                      // reduction MMA complete (ENC_NODE / DEC) or E3 done (ENC_EDGE)
+                    cmark(0, g);
                     // (bulk-copy groups belong to the issuing thread: elect.sync picks the same lane every time)
                     if (MODE == EDGE_ENC_EDGE) {
                         if (elect_one()) {
@@ -210,6 +223,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     if (t + tile_stride < tile_end) {
                         if (MODE == EDGE_ENC_EDGE) { if (elect_one()) tma_store_wait_read(); __syncwarp(); }   // the store has finished reading the tile
                         issue_load(g, t + tile_stride);
+                        cmark(1, g);
                     }
                 }
                 ph_go ^= 1;
@@ -247,34 +261,72 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             };
             mbar_wait(smem_u32(&sBar[0]), 0);                         // weights resident
             uint32_t round = 0;
-            for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride, ++round) {
-                const int n = min(4, tile_end - t0);                   // live slots of this round
-                const int n_next = max(0, min(4, tile_end - (t0 + tile_stride)));
-                if (round == 0)
-                    for (int g = 0; g < n; ++g) { mbar_wait(bar_load(g), 0); issue_mma(g, 0); }                // TMA landed -> MMA 1
-                for (int g = 0; g < n; ++g) { mbar_wait(bar_epi(g), ph_epi); issue_mma(g, 1); }                // E1 done -> MMA 2
-                ph_epi ^= 1;
-                for (int g = 0; g < n; ++g) {                                                                  // E2 done -> reduction MMA / MMA 3
-                    mbar_wait(bar_epi(g), ph_epi);
-                    if (MODE == EDGE_ENC_EDGE) { issue_mma(g, 2); if (elect_one()) umma_commit(bar_m3(g)); __syncwarp(); } else issue_reduce(g);
-                }
-                ph_epi ^= 1;
-                // E3 done: the accumulator is drained -> MMA 1 of the slot's next tile as soon as its TMA has landed.
-                // ENC_EDGE recycles the operand tile only now (store, then reload), so its MMA 1 trails by one slot.
-                const uint32_t next_parity = (round + 1) & 1;
-                for (int g = 0; g < n; ++g) {
-                    if (MODE == EDGE_ENC_EDGE) {
+            if (MODE == EDGE_ENC_EDGE) {
+                for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride, ++round) {
+                    const int n = min(4, tile_end - t0);                   // live slots of this round
+                    const int n_next = max(0, min(4, tile_end - (t0 + tile_stride)));
+                    if (round == 0)
+                        for (int g = 0; g < n; ++g) { mbar_wait(bar_load(g), 0); issue_mma(g, 0); }            // TMA landed -> MMA 1
+                    for (int g = 0; g < n; ++g) { mbar_wait(bar_epi(g), ph_epi); cmark(0, g); issue_mma(g, 1); cmark(1, g); }   // E1 done -> MMA 2
+                    ph_epi ^= 1;
+                    for (int g = 0; g < n; ++g) {                                                              // E2 done -> MMA 3
                         mbar_wait(bar_epi(g), ph_epi);
-                        if (elect_one()) mbar_arrive(bar_go(g));                                               // tile complete in smem: store + recycle
+                        cmark(2, g);
+                        issue_mma(g, 2);
+                        if (elect_one()) umma_commit(bar_m3(g));
                         __syncwarp();
-                    } else {
-                        mbar_wait(smem_u32(&sBar[25 + g]), round & 1);                                         // reduced sums read out of TMEM
                     }
-                    const int h = MODE == EDGE_ENC_EDGE ? g - 1 : g;
-                    if (h >= 0 && h < n_next) { mbar_wait(bar_load(h), next_parity); issue_mma(h, 0); }
+                    ph_epi ^= 1;
+                    // E3 done: the tile is complete in shared memory and the accumulator is drained.  The TMA warp stores the tile
+                    // and only then reloads the slot, so the slot's next MMA 1 trails by one slot.
+                    const uint32_t next_parity = (round + 1) & 1;
+                    for (int g = 0; g < n; ++g) {
+                        mbar_wait(bar_epi(g), ph_epi);
+                        if (elect_one()) mbar_arrive(bar_go(g));                                               // store + recycle
+                        __syncwarp();
+                        cmark(3, g);
+                        if (g >= 1 && g - 1 < n_next) { mbar_wait(bar_load(g - 1), next_parity); cmark(4, g - 1); issue_mma(g - 1, 0); cmark(5, g - 1); }
+                    }
+                    if (n - 1 < n_next) { mbar_wait(bar_load(n - 1), next_parity); issue_mma(n - 1, 0); }
+                    ph_epi ^= 1;
                 }
-                if (MODE == EDGE_ENC_EDGE && n - 1 < n_next) { mbar_wait(bar_load(n - 1), next_parity); issue_mma(n - 1, 0); }
-                if (MODE == EDGE_ENC_EDGE) ph_epi ^= 1;
+            } else {
+                // ENC_NODE / DEC.  A slot's next tile is started as soon as it can be: right after the NEXT slot's reduction has been
+                // issued (by then the drain warps have read the slot's sums and its reload, requested when its own reduction
+                // completed, has landed) -- not after the round's last reduction, which left the epilogue warps idle at every round
+                // boundary.  Slot 3's turn comes after the first MMA 2 of the following round (its drain rides behind E1 of slot 0).
+                bool pend3 = false;                                    // slot 3 of the previous round still has to be restarted
+                uint32_t pend_round = 0;
+                auto restart = [&](int h, uint32_t rnd) {              // next tile of slot h; rnd = round of the tile that just finished
+                    mbar_wait(smem_u32(&sBar[25 + h]), rnd & 1);       // reduced sums read out of TMEM
+                    cmark(3, h);
+                    mbar_wait(bar_load(h), (rnd + 1) & 1);
+                    cmark(4, h);
+                    issue_mma(h, 0);
+                    cmark(5, h);
+                };
+                for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride, ++round) {
+                    const int n = min(4, tile_end - t0);
+                    const int n_next = max(0, min(4, tile_end - (t0 + tile_stride)));
+                    if (round == 0)
+                        for (int g = 0; g < n; ++g) { mbar_wait(bar_load(g), 0); issue_mma(g, 0); }
+                    for (int g = 0; g < n; ++g) {                                                              // E1 done -> MMA 2
+                        mbar_wait(bar_epi(g), ph_epi); cmark(0, g); issue_mma(g, 1); cmark(1, g);
+                        if (g == 0 && pend3) { restart(3, pend_round); pend3 = false; }
+                    }
+                    ph_epi ^= 1;
+                    for (int g = 0; g < n; ++g) {                                                              // E2 done -> reduction MMA
+                        mbar_wait(bar_epi(g), ph_epi);
+                        cmark(2, g);
+                        issue_reduce(g);
+                        if (g >= 1 && g - 1 < n_next) restart(g - 1, round);
+                    }
+                    ph_epi ^= 1;
+                    if (n - 1 < n_next) {
+                        if (n == 4) { pend3 = true; pend_round = round; }
+                        else restart(n - 1, round);
+                    }
+                }
             }
         }
     } else {
@@ -337,7 +389,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         };
 
-        unsigned long long* trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
+        unsigned long long* trace = (p.trace != nullptr && p.trace_epi && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
         int n_trace = 0;
         auto mark = [&](int ev, int s) {               // debug timeline (off unless the plan's "tc_trace" buffer was requested)
             if (trace != nullptr && n_trace < 500) {
@@ -602,6 +654,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     tp.n_tiles = tp.tiles_per_member * p.NB;
     tp.lengths = p.lengths; tp.frame_of = p.frame_of; tp.nbr_idx = p.nbr_idx; tp.S = p.S;
     tp.trace = p.tc_trace; tp.trace_slot = p.launches & 2047;
+    { static const bool ctrl_only = getenv("CB2_TRACE_CTRL_ONLY") != nullptr; tp.trace_epi = ctrl_only ? 0 : 1; }
     const bool first = (layer == 0 && mode != EDGE_DEC);
     tp.in_is_frame = first ? 1 : 0;
     tp.single_frame = p.F == 1 ? 1 : 0;
