@@ -379,7 +379,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             return (meta_tin(m) * NPT + q_of_r < len && meta_j(m) < len) ? 0xffffffffu : 0u;
         };
         auto ld_pc = [&](const TileMeta& m, uint32_t (&pc)[16]) {       // this thread's 32 gathered halves of Pc[j]
+#ifdef CB2_X_NOGATHER
+            const __half* src = p.P16 + 128 + c0;
+#else
             const __half* src = p.P16 + ((size_t)meta_member(m) * p.L + meta_j(m)) * 256 + 128 + c0;
+#endif
             ldg256(src, *reinterpret_cast<uint32_t(*)[8]>(&pc[0]));
             ldg256(src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[8]));
         };
@@ -456,7 +460,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 tc_fence_after();
                 mark(1, s);
                 float acc0[16], acc1[16];
+#ifdef CB2_X_NOLDTM                                                     // timing ablations (scratch/build_variant.sh), never in the product build
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));
+                    asm volatile("mov.b32 %0, %1;" : "=f"(acc1[e]) : "r"(tid - e));
+                }
+#else
                 tmem_ld16x2(tmem_lane + (uint32_t)(s * 128), acc0, acc1);
+#endif
 #pragma unroll
                 for (int g16 = 0; g16 < 2; ++g16) {
                     const float (&acc)[16] = g16 ? acc1 : acc0;
@@ -466,7 +478,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(pa[g16 * 8 + e])), as_h2(pc[g16 * 8 + e]));
                         o[e] = as_u32(gelu2_h2(x));
                     }
+#ifdef CB2_X_NOSTS
+                    if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, g16, o);
+#else
                     st16(T, g16, o);
+#endif
                 }
                 mark(2, s);
                 stage_done(s, true);
@@ -495,7 +511,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     tc_fence_after();
                     mark(5, s);
                     float acc0[16], acc1[16];
+#ifdef CB2_X_NOLDTM
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));
+                        asm volatile("mov.b32 %0, %1;" : "=f"(acc1[e]) : "r"(tid - e));
+                    }
+#else
                     tmem_ld16x2(tmem_lane + (uint32_t)(s * 128), acc0, acc1);
+#endif
 #pragma unroll
                     for (int g16 = 0; g16 < 2; ++g16) {
                         const float (&acc)[16] = g16 ? acc1 : acc0;
@@ -505,7 +529,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             const __half2 x = __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(bb[g16 * 8 + e]));
                             o[e] = as_u32(gelu2_h2(x)) & keep;
                         }
+#ifdef CB2_X_NOSTS
+                        if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, g16, o);
+#else
                         st16(T, g16, o);
+#endif
                     }
                     mark(6, s);
                     stage_done(s, true);
