@@ -37,5 +37,6 @@ print("launch windows:", len(st), " span us", (en[-1] - t0) / 1e3, " sum of wind
 for i in range(800, 840):
     print(f"{(st[i] - t0) / 1e3:9.2f} .. {(en[i] - t0) / 1e3:9.2f}   dur {dur[i]:6.2f}   gap before {0 if i == 0 else gaps[i - 1]:6.2f}")
 # per-step summary from end-to-end deltas
-ends = en[800:800 + 17]
-print("end deltas:", np.diff(ends / 1e3).round(1).tolist(), " step us", (en[816] - en[800]) / 1e3)
+nps = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+ends = en[50 * nps:50 * nps + nps + 1]
+print("end deltas:", np.diff(ends / 1e3).round(1).tolist(), " step us", (ends[-1] - ends[0]) / 1e3)
