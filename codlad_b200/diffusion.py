@@ -59,11 +59,13 @@ class SpacedDiffusion:
     """Respaced DDPM with epsilon prediction and learned-range variance (the configuration
     create_diffusion builds for test.py:298-303).  Attribute names follow the reference."""
 
-    def __init__(self, use_timesteps, betas, learn_sigma=True, predict_xstart=False, sigma_small=False, self_condition=False):
+    def __init__(self, use_timesteps, betas, learn_sigma=True, predict_xstart=False, sigma_small=False, self_condition=False,
+                 loss_type="mse"):
         if predict_xstart or not learn_sigma or self_condition:
             raise NotImplementedError("codlad_b200 implements the sampling configuration of the reference's inference "
                                       "script: epsilon prediction, learn_sigma=True, no self-conditioning")
         self.use_timesteps = set(use_timesteps)
+        self.loss_type = loss_type
         base = np.array(betas, dtype=np.float64)
         self.original_num_steps = len(base)
         base_ac = np.cumprod(1.0 - base, axis=0)
@@ -178,8 +180,70 @@ class SpacedDiffusion:
         mean = c[..., 4] * pred_xstart + c[..., 5] * x
         return {"mean": mean, "variance": torch.exp(log_variance), "log_variance": log_variance, "pred_xstart": pred_xstart}
 
-    def training_losses(self, *a, **k):
-        raise NotImplementedError("train_latent step (SURVEY.md section 8, row f-1) is not part of this round")
+    # -- loss values (evaluation only: the CUDA denoiser has no backward, so there is no training step here) ---------
+    def _table_on(self, name, t, ndim):
+        key = (name, str(t.device))
+        if key not in self._coef_dev:
+            self._coef_dev[key] = torch.from_numpy(getattr(self, name)).to(t.device).float()     # .float() as gaussian_diffusion.py:737
+        return self._coef_dev[key][t].view(-1, *([1] * (ndim - 1)))
+
+    def q_sample(self, x_start, t, noise=None):
+        """gaussian_diffusion.py:223-238: x_t ~ q(x_t | x_0)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return (self._table_on("sqrt_alphas_cumprod", t, x_start.dim()) * x_start
+                + self._table_on("sqrt_one_minus_alphas_cumprod", t, x_start.dim()) * noise)
+
+    def q_posterior_mean_variance(self, x_start, x_t, t):
+        """gaussian_diffusion.py:240-260: mean, variance and clipped log-variance of q(x_{t-1} | x_t, x_0)."""
+        d = x_t.dim()
+        mean = self._table_on("posterior_mean_coef1", t, d) * x_start + self._table_on("posterior_mean_coef2", t, d) * x_t
+        shape = x_t.shape
+        return (mean, self._table_on("posterior_variance", t, d).expand(shape),
+                self._table_on("posterior_log_variance_clipped", t, d).expand(shape))
+
+    @staticmethod
+    def _mean_flat(x, mask=None):
+        dims = list(range(1, x.dim()))
+        return x.mean(dim=dims) if mask is None else (x * mask).sum(dim=dims) / mask.sum(dim=dims)      # gaussian_diffusion.py:16-26
+
+    def _vb_terms_bpd(self, model, x_start, x_t, t, mask=None):
+        """gaussian_diffusion.py:549-596: KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)) in bits, the discretised decoder NLL at t = 0."""
+        true_mean, _, true_logvar = self.q_posterior_mean_variance(x_start, x_t, t)
+        out = self.p_mean_variance(model, x_t, t, clip_denoised=False)
+        lv = out["log_variance"]
+        kl = 0.5 * (-1.0 + lv - true_logvar + torch.exp(true_logvar - lv) + (true_mean - out["mean"]) ** 2 * torch.exp(-lv))   # diffusion_utils.py:10-37
+        m = None if mask is None else mask.unsqueeze(-1).expand_as(x_start)
+        kl = self._mean_flat(kl, m) / math.log(2.0)
+        # discretised Gaussian log-likelihood, diffusion_utils.py:62-88 (tanh approximation of the normal CDF, bin half-width 1/255)
+        cdf = lambda v: 0.5 * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (v + 0.044715 * torch.pow(v, 3))))
+        centered, inv_std = x_start - out["mean"], torch.exp(-0.5 * lv)
+        cdf_plus, cdf_min = cdf(inv_std * (centered + 1.0 / 255.0)), cdf(inv_std * (centered - 1.0 / 255.0))
+        log_probs = torch.where(x_start < -0.999, torch.log(cdf_plus.clamp(min=1e-12)),
+                                torch.where(x_start > 0.999, torch.log((1.0 - cdf_min).clamp(min=1e-12)),
+                                            torch.log((cdf_plus - cdf_min).clamp(min=1e-12))))
+        nll = self._mean_flat(-log_probs, m) / math.log(2.0)
+        return {"output": torch.where(t == 0, nll, kl), "pred_xstart": out["pred_xstart"]}
+
+    def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
+        """gaussian_diffusion.py:598-725 for the shipped configuration (epsilon prediction, learned-range variance, MSE loss +
+        VB term on the frozen mean): dict(mse, vb, loss), each [B].  Values only -- use it to score a checkpoint; `train_latent`
+        itself needs the backward pass of the denoiser, which this package does not have."""
+        model_kwargs = dict(model_kwargs or {})
+        model_kwargs.pop("epoch", None)
+        noise = torch.randn_like(x_start) if noise is None else noise
+        x_t = self.q_sample(x_start, t, noise)
+        map_t = torch.tensor(self.timestep_map, device=t.device, dtype=t.dtype)[t]     # respace.py:124-125
+        out = model(x_t, map_t, **model_kwargs).to(torch.float32)
+        C_ = x_t.shape[-1]
+        if out.shape != (*x_t.shape[:-1], 2 * C_):
+            raise ValueError(f"model output {tuple(out.shape)}, expected {(*x_t.shape[:-1], 2 * C_)}")
+        mask = model_kwargs.get("mask")
+        vb = self._vb_terms_bpd(lambda *a, **k: out, x_start, x_t, t, mask)["output"]
+        if self.loss_type == "rescaled_mse":
+            vb = vb * (self.num_timesteps / 1000.0)
+        diff2 = (noise - out[..., :C_]) ** 2
+        mse = self._mean_flat(diff2, None if mask is None else mask.unsqueeze(-1).expand_as(diff2))
+        return {"mse": mse, "vb": vb, "loss": mse + vb}
 
 
 def create_diffusion(timestep_respacing, noise_schedule="linear", use_kl=False, rescale_learned_sigmas=False,
@@ -188,5 +252,8 @@ def create_diffusion(timestep_respacing, noise_schedule="linear", use_kl=False, 
     if timestep_respacing is None or timestep_respacing == "":
         timestep_respacing = [diffusion_steps]
     betas = get_named_beta_schedule(noise_schedule, diffusion_steps)
+    if use_kl:
+        raise NotImplementedError("the KL loss type is not used by the reference's training script")
     return SpacedDiffusion(space_timesteps(diffusion_steps, timestep_respacing), betas, learn_sigma=learn_sigma,
-                           predict_xstart=predict_xstart, sigma_small=sigma_small, self_condition=self_condition)
+                           predict_xstart=predict_xstart, sigma_small=sigma_small, self_condition=self_condition,
+                           loss_type="rescaled_mse" if rescale_learned_sigmas else "mse")

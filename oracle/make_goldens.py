@@ -178,6 +178,28 @@ def golden_ic_large_angle(name, L, seed):
     print(name, tuple(xyz.shape))
 
 
+def golden_training_losses(name, B, L, seed):
+    """training_losses of the unmodified reference (gaussian_diffusion.py:549-725, MSE loss + learned-range VB term) for a fixed
+    "model output": pins q_sample, the posterior, normal_kl, the discretised likelihood and the masked means.  Inputs are
+    re-derived from the seed by the test (same generator calls)."""
+    diffusion = create_diffusion(timestep_respacing="")                  # training uses the unspaced 1000-step chain
+    g = torch.Generator().manual_seed(seed)
+    x_start = torch.randn(B, L, 3, generator=g)
+    noise = torch.randn(B, L, 3, generator=g)
+    model_out = 0.7 * torch.randn(B, L, 6, generator=g)
+    t = torch.tensor([0, 1, 500, 999, 37, 0][:B])
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[1, L - 5:] = False
+    mask[-1, L // 2:] = False
+    model = lambda x_t, tt, **kw: model_out
+    with torch.no_grad():
+        terms = diffusion.training_losses(model, x_start, t, dict(mask=mask), noise=noise)
+        terms_nomask = diffusion.training_losses(model, x_start, t, dict(), noise=noise)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), mse=terms["mse"].numpy(), vb=terms["vb"].numpy(), loss=terms["loss"].numpy(),
+                        loss_nomask=terms_nomask["loss"].numpy(), meta=np.array([B, L, seed]))
+    print(name, terms["loss"].tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -193,6 +215,7 @@ def main():
     golden_decode("decode_L64_N6_c2", 64, 1, 1001, 4003, False, use_c2=True)
     golden_vq("vq_20000", 20000, 5001)
     golden_ic_large_angle("ic_large_angle_L48", 48, 6001)
+    golden_training_losses("training_losses_B6", 6, 24, 7001)
 
 
 if __name__ == "__main__":

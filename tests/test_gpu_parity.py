@@ -484,3 +484,28 @@ def test_whole_path_at_large_config_shapes(eng, L, K, frames, ens):
     table = vsd["equivaraintconv.backbone_dist.weight"]
     cg_z = fs.cg_z.long()[fs.frame_of.long()]
     assert torch.equal(ic[:, :, :3, 0], table[cg_z]), "backbone bond lengths are a table lookup"
+
+
+def test_training_losses_with_cuda_denoiser(R):
+    """Validation loss as train_latent computes it (train_latent.py:208: diffusion.training_losses(model, x, t, model_kwargs)),
+    with the CUDA denoiser behind the reference module surface, against the same formulas fed with the oracle's forward."""
+    from codlad_b200.diffusion import create_diffusion
+    from codlad_b200.latent_model import MPNN_models
+    dsd = weights.init_denoiser_state(5)
+    model = MPNN_models["mpnn_diffusion"](input_size=3, unconditional=True, diffusion="diffusion", precision="fp32")
+    model.load_state_dict(dsd)
+    diffusion = create_diffusion("")
+    L, Fr = 48, 3
+    prot = synthetic.make_protein(L, Fr, seed=4343)
+    batch = synthetic.collate(prot)
+    mask = torch.ones(Fr, L, dtype=torch.bool)
+    x0 = synthetic.latent_noise((Fr, L, 3), 17)
+    noise = synthetic.latent_noise((Fr, L, 3), 18)
+    t = torch.tensor([0, 412, 999])
+    terms = diffusion.training_losses(model.forward, x0.cuda(), t.cuda(), dict(y=None, mask=mask.cuda(), batch=batch), noise=noise.cuda())
+    X = prot.ca_full[:, 1:-1].contiguous()
+    zz = prot.restype_full[1:-1][None].expand(Fr, -1)
+    ref_model = lambda x_t, tt, **kw: R.denoiser_forward(dsd, x_t, tt, X, zz, mask, 64)
+    ref = diffusion.training_losses(ref_model, x0, t, dict(mask=mask), noise=noise)
+    for k in ("mse", "vb", "loss"):
+        assert torch.allclose(terms[k].cpu(), ref[k], rtol=1e-3, atol=1e-5), (k, terms[k], ref[k])

@@ -121,3 +121,28 @@ def test_p_mean_variance_matches_oracle_update():
         ref = R.p_sample_update(x, out, step, noise, sched)
         assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6), step
         assert torch.allclose(pmv["variance"], torch.exp(pmv["log_variance"]))
+
+
+def test_training_losses_values_match_reference_golden():
+    """training_losses / q_sample / posterior / VB terms against the golden written by the unmodified reference
+    (oracle/make_goldens.py::golden_training_losses): loss values only, the package has no backward pass."""
+    import os
+    from codlad_b200.diffusion import create_diffusion
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "training_losses_B6.npz"))
+    B, L, seed = (int(v) for v in g["meta"])
+    diff = create_diffusion(timestep_respacing="")
+    assert diff.num_timesteps == 1000
+    gen = torch.Generator().manual_seed(seed)
+    x_start = torch.randn(B, L, 3, generator=gen)
+    noise = torch.randn(B, L, 3, generator=gen)
+    model_out = 0.7 * torch.randn(B, L, 6, generator=gen)
+    t = torch.tensor([0, 1, 500, 999, 37, 0][:B])
+    mask = torch.ones(B, L, dtype=torch.bool)
+    mask[1, L - 5:] = False
+    mask[-1, L // 2:] = False
+    model = lambda x_t, tt, **kw: model_out
+    terms = diff.training_losses(model, x_start, t, dict(mask=mask), noise=noise)
+    for k in ("mse", "vb", "loss"):
+        assert torch.allclose(terms[k], torch.from_numpy(g[k]), rtol=2e-5, atol=1e-6), k
+    nomask = diff.training_losses(model, x_start, t, {}, noise=noise)
+    assert torch.allclose(nomask["loss"], torch.from_numpy(g["loss_nomask"]), rtol=2e-5, atol=1e-6)
