@@ -1,0 +1,116 @@
+"""Sample-quality metrics of the evaluation step that follows sampling: the reference's
+`eval_sample_qualities` (utils/protein_module.py:335-364) and `valid_ratio_and_cut_off_result` (test.py:168-188) on the
+GPU.  The O(Na^2) bond-graph comparison and the RMSD sums run in libcodlad_b200.so (`cb2_eval_bond_graphs`); the elementwise
+losses of test.py:97-166 are restated with torch ops on whatever device their inputs live on.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+EPS = 1e-7      # test.py:27
+# COVCUTOFFTABLE (utils/protein_module.py:128-): covalent radii in Angstrom used for the bond cut-off; the elements proteins contain
+COV_RADIUS = {1: 0.23, 6: 0.68, 7: 0.68, 8: 0.68, 15: 0.75, 16: 1.02, 34: 1.22}
+MAX_Z = max(COV_RADIUS)
+_RADII_DEV = {}
+
+
+def _radius_table(extra=None) -> torch.Tensor:
+    table = dict(COV_RADIUS)
+    table.update(extra or {})
+    t = torch.zeros(max(table) + 1, dtype=torch.float32)
+    for z, r in table.items():
+        t[z] = r
+    return t
+
+
+def bond_graph_stats(xyz_ref: torch.Tensor, xyz_gen: torch.Tensor, atomic_nums: torch.Tensor, num_atoms, scale: float = 1.3, radii=None):
+    """Raw per-structure statistics.  xyz_* [sum Na, 3], atomic_nums [sum Na], num_atoms [n] -> (counts [n, 6] int64, sums [n, 4] f64)
+    on the device: counts = {differing adjacency entries, reference bonds, generated bonds} for all atoms, then heavy atoms only;
+    sums = {sum of squared deviations, Na, the same over heavy atoms, number of heavy atoms}."""
+    N.require_cuda()
+    dev = xyz_gen.device if xyz_gen.is_cuda else torch.device("cuda")
+    ref = xyz_ref.to(dev, torch.float32).contiguous()
+    gen = xyz_gen.to(dev, torch.float32).contiguous()
+    z = atomic_nums.to(dev, torch.int32).contiguous()
+    num = torch.as_tensor(num_atoms, dtype=torch.int64).cpu()
+    if ref.shape != gen.shape or ref.shape[0] != z.shape[0] or int(num.sum()) != ref.shape[0]:
+        raise ValueError("xyz_ref / xyz_gen / atomic_nums / num_atoms do not describe the same atoms")
+    unknown = set(int(v) for v in torch.unique(z).tolist()) - set(COV_RADIUS) - set(radii or {})
+    if unknown:
+        raise KeyError(f"no covalent radius for atomic numbers {sorted(unknown)}")
+    offsets = torch.zeros(num.numel() + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(num, 0)
+    key = (str(dev), tuple(sorted((radii or {}).items())))
+    rad = _RADII_DEV.get(key)
+    if rad is None:
+        rad = _RADII_DEV[key] = _radius_table(radii).to(dev)
+    n = int(num.numel())
+    counts = torch.empty(n, 6, dtype=torch.int64, device=dev)
+    sums = torch.empty(n, 4, dtype=torch.float64, device=dev)
+    off_dev = offsets.to(dev, non_blocking=True)
+    N.check(N.lib().cb2_eval_bond_graphs(N.dptr(ref), N.dptr(gen), N.dptr(z), N.dptr(off_dev), n, int(num.max()) if n else 0, N.dptr(rad),
+                                         int(rad.numel() - 1), C.c_float(scale), N.dptr(counts), N.dptr(sums), N.stream_ptr()), "eval_bond_graphs")
+    return counts, sums
+
+
+def eval_sample_qualities(xyz_ref, xyz_gen, atomic_nums, num_atoms, scale: float = 1.3):
+    """Per structure (one generated structure per reference structure, as test.py:178-181 calls it): dict of tensors
+    `heavy_valid`, `all_valid` (bond graph identical to the reference's), `heavy_graph_diff_ratio`, `all_graph_diff_ratio`
+    (|#ref bonds - #gen bonds| / #ref bonds, protein_module.py:315), `all_rmsd`, `heavy_rmsd` (protein_module.py:325-333)."""
+    counts, sums = bond_graph_stats(xyz_ref, xyz_gen, atomic_nums, num_atoms, scale)
+    c = counts.to(torch.float64)
+    return {
+        "all_valid": counts[:, 0] == 0, "heavy_valid": counts[:, 3] == 0,
+        "all_graph_diff_ratio": (c[:, 1] - c[:, 2]).abs() / c[:, 1], "heavy_graph_diff_ratio": (c[:, 4] - c[:, 5]).abs() / c[:, 4],
+        "all_rmsd": torch.sqrt(sums[:, 0] / sums[:, 1]), "heavy_rmsd": torch.sqrt(sums[:, 2] / sums[:, 3]),
+    }
+
+
+def valid_ratio_and_cut_off_result(xyz, xyz_recon, num_atoms, atomic_nums):
+    """test.py:168-188: four per-structure lists (heavy valid ratio, all-atom valid ratio, heavy graph-difference ratios,
+    all-atom graph-difference ratios); each structure is compared with its single reconstruction, so a ratio is 0.0 or 1.0 and
+    the difference lists hold one-element lists."""
+    q = eval_sample_qualities(xyz, xyz_recon, atomic_nums, num_atoms)
+    hv, av = q["heavy_valid"].cpu().tolist(), q["all_valid"].cpu().tolist()
+    hg, ag = q["heavy_graph_diff_ratio"].cpu().tolist(), q["all_graph_diff_ratio"].cpu().tolist()
+    return [float(v) for v in hv], [float(v) for v in av], [[float(v)] for v in hg], [[float(v)] for v in ag]
+
+
+# -- elementwise evaluation losses (test.py:97-166); torch ops on the inputs' device ------------------------------------------
+def _pair_dist(xyz, pairs):
+    return ((xyz[pairs[:, 0]] - xyz[pairs[:, 1]]).pow(2).sum(-1) + EPS).sqrt()
+
+
+def ged_result(xyz_recon, xyz, edge_list):
+    """test.py:141-146: mean squared difference of the bonded distances."""
+    return (_pair_dist(xyz_recon, edge_list) - _pair_dist(xyz, edge_list)).pow(2).mean()
+
+
+def xyz_result(xyz_recon, xyz):
+    """test.py:148-151."""
+    return (xyz_recon - xyz).pow(2).sum(-1).mean()
+
+
+def clash_result(edge_list, nbr_list, xyz_recon, bb_NO_list):
+    """test.py:118-139: fraction of non-bonded neighbour pairs (rows occurring once in cat(edge_list, nbr_list)) closer than
+    1.2 A plus the same fraction over the backbone N-O pairs."""
+    combined = torch.cat((edge_list, nbr_list))
+    uniques, counts = combined.unique(dim=0, return_counts=True)
+    d = _pair_dist(xyz_recon, uniques[counts == 1])
+    zero = torch.zeros((), device=xyz_recon.device)
+    loss = (d < 1.2).sum().float() / d.numel() if d.numel() > 0 else zero
+    b = _pair_dist(xyz_recon, bb_NO_list)
+    return loss + ((b < 1.2).sum().float() / b.numel() if b.numel() > 0 else zero)
+
+
+def recon_result(ic_recon, ic, mask_):
+    """test.py:153-166: bond MSE and chord-length angle / torsion errors over the real atoms."""
+    m = torch.cat([mask_])
+    n = m.sum()
+    bond = ((ic_recon[:, :, 0] - ic[:, :, 0]).reshape(-1) * m).pow(2).sum() / n
+    chord = lambda k: ((2 * (1 - torch.cos(ic[:, :, k] - ic_recon[:, :, k])) + EPS).sqrt().reshape(-1) * m).sum() / n
+    return bond, chord(1), chord(2)

@@ -137,6 +137,17 @@ CB2_API int cb2_ic_to_xyz(const float* ca_full, const float* ic_recon, int NB, i
                   const int* lengths, const signed char* atom_orders, const int* slot_atom,
                   const long long* out_offset, float* xyz, void* stream);
 
+/* ---- evaluation step right after the path --------------------------------------------------
+ * Replaces: eval_sample_qualities / count_valid_graphs / get_bond_graphs / compute_rmsd (utils/protein_module.py:245-364),
+ * called per structure by valid_ratio_and_cut_off_result (test.py:168-188) with two dense [Na, Na] matrices on the CPU.
+ * All pointers are DEVICE: xyz_ref / xyz_gen [sum Na, 3], atomic_num [sum Na], offsets [n_struct + 1] (atom ranges of the
+ * structures), cov_radius [max_z + 1] (COVCUTOFFTABLE, protein_module.py:128); max_atoms = the largest structure.  Outputs:
+ *   counts [n_struct, 6] = {differing adjacency entries, reference bonds, generated bonds} over all atoms, then over heavy atoms
+ *   sums   [n_struct, 4] = {sum ||x_gen - x_ref||^2 over all atoms, Na, the same over heavy atoms, number of heavy atoms}
+ * bond(i, j) = i != j and ||x_i - x_j|| < (r[z_i] + r[z_j]) * scale in fp32, entries counted over the full symmetric matrix. */
+CB2_API int cb2_eval_bond_graphs(const float* xyz_ref, const float* xyz_gen, const int* atomic_num, const long long* offsets, int n_struct,
+                         int max_atoms, const float* cov_radius, int max_z, float scale, long long* counts, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -200,6 +200,51 @@ def golden_training_losses(name, B, L, seed):
     print(name, terms["loss"].tolist())
 
 
+def synthetic_all_atom(L, frames, seed, sigma):
+    """Reference / generated all-atom structures for the metric goldens: the reference structure is the synthetic protein rebuilt
+    from seeded internal coordinates by the reference's own ic_to_xyz; the generated one is that structure plus N(0, sigma) noise
+    (bonds break as sigma grows).  Atomic numbers: N, CA, C, O backbone, carbon / sulphur side chains by slot parity."""
+    prot = synthetic.make_protein(L, frames, seed=seed)
+    batch = synthetic.collate(prot)
+    g = torch.Generator().manual_seed(seed + 1)
+    ic = torch.stack([1.2 + 0.4 * torch.rand(frames * L, 13, generator=g), 1.8 + 0.5 * torch.rand(frames * L, 13, generator=g),
+                      6.28 * torch.rand(frames * L, 13, generator=g) - 3.14], -1)
+    with torch.no_grad():
+        xyz = ic_to_xyz(batch["OG_CG_nxyz"].reshape(-1, L + 2, 4), ic.reshape(frames, L, 13, 3), prot.info)     # [frames, Na, 3]
+    na = xyz.shape[1]
+    z = torch.tensor([7, 6, 6, 8] + [6, 16, 1, 6, 8, 7, 1, 6, 1, 6], dtype=torch.int64).repeat((na + 13) // 14)[:na]
+    gen = xyz + sigma * torch.randn(xyz.shape, generator=g)
+    return xyz.reshape(-1, 3), gen.reshape(-1, 3), z.repeat(frames), [na] * frames
+
+
+def golden_sample_qualities(name, L, frames, seed, sigma):
+    """eval_sample_qualities of the unmodified reference (utils/protein_module.py:335-364), one reconstruction per structure as
+    test.py:178-181 calls it.  ASE is absent here: a 3-method stand-in for ase.Atoms is injected into the reference module."""
+    import utils.protein_module as pm
+
+    class Atoms:
+        def __init__(self, numbers, positions):
+            self.z, self.x = np.asarray(numbers), np.asarray(positions, dtype=np.float64)
+        def get_positions(self): return self.x
+        def get_atomic_numbers(self): return self.z
+        def __len__(self): return len(self.z)
+
+    pm.Atoms = Atoms
+    ref, gen, z, num = synthetic_all_atom(L, frames, seed, sigma)
+    out, o = [], 0
+    for na in num:
+        ra = Atoms(z[o:o + na].numpy(), ref[o:o + na].numpy())
+        ga = Atoms(z[o:o + na].numpy(), gen[o:o + na].numpy())
+        all_rmsds, heavy_rmsds, vr, var, gvr, gavr = pm.eval_sample_qualities(ra, [ga])
+        rm = pm.compute_rmsd([ga], ra, [0])[0]
+        out.append([vr, var, gvr[0], gavr[0], rm[0], rm[1]])
+        o += na
+    # (the structures come out of the reference's ic_to_xyz, so -- unlike the other goldens -- the inputs are stored too)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), q=np.array(out, dtype=np.float64), meta=np.array([L, frames, seed]), sigma=np.array(sigma),
+                        xyz_ref=ref.numpy(), xyz_gen=gen.numpy(), z=z.numpy().astype(np.int16), num_atoms=np.array(num))
+    print(name, np.array(out).round(4).tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -216,6 +261,8 @@ def main():
     golden_vq("vq_20000", 20000, 5001)
     golden_ic_large_angle("ic_large_angle_L48", 48, 6001)
     golden_training_losses("training_losses_B6", 6, 24, 7001)
+    golden_sample_qualities("sample_qualities_exact", 40, 2, 8001, 0.0)
+    golden_sample_qualities("sample_qualities_noisy", 40, 3, 8002, 0.08)
 
 
 if __name__ == "__main__":

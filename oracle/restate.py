@@ -504,3 +504,38 @@ def ic_to_xyz(CG_nxyz, ic_recon, info):
     slots = ic_to_slots(CG_nxyz[:, :, 1:], ic_recon, atom_orders)
     flat = slots.reshape(slots.shape[0], -1, 3)
     return flat[:, atom_idx][:, permute]
+
+# --------------------------------------------------------------------------------------
+# Evaluation step after the path
+# --------------------------------------------------------------------------------------
+COV_RADIUS = {1: 0.23, 6: 0.68, 7: 0.68, 8: 0.68, 15: 0.75, 16: 1.02, 34: 1.22}     # COVCUTOFFTABLE, utils/protein_module.py:128-
+
+
+def bond_graph(xyz, z, scale=1.3):
+    """get_bond_graphs (utils/protein_module.py:279-288): dense boolean adjacency, dist < (r_i + r_j) * scale, zero diagonal.
+    fp32 like the reference (torch.Tensor(positions)); the square root is the correctly rounded one (see sqrt_rn)."""
+    xyz = xyz.to(torch.float32)
+    r = torch.tensor([COV_RADIUS[int(v)] for v in z.tolist()], dtype=torch.float32)
+    dist = sqrt_rn((xyz[:, None, :] - xyz[None, :, :]).pow(2).sum(-1))
+    bond = dist < (r[None, :] + r[:, None]) * scale
+    bond.fill_diagonal_(False)
+    return bond
+
+
+def sample_quality_stats(xyz_ref, xyz_gen, z, num_atoms, scale=1.3):
+    """What eval_sample_qualities (utils/protein_module.py:335-364) derives its outputs from, per structure:
+    counts [n, 6] = {#entries where the graphs differ, #ref bonds, #gen bonds} for all atoms, then for heavy atoms only
+    (dropH, :266-277), and sums [n, 4] = {sum of squared deviations, Na, the same over heavy atoms, #heavy} (compute_rmsd, :319-333)."""
+    counts, sums, o = [], [], 0
+    for na in [int(v) for v in num_atoms]:
+        r, g, zz = xyz_ref[o:o + na], xyz_gen[o:o + na], z[o:o + na]
+        heavy = zz != 1
+        row = []
+        for sel in (torch.ones_like(heavy), heavy):
+            br, bg = bond_graph(r[sel], zz[sel], scale), bond_graph(g[sel], zz[sel], scale)
+            row += [int((br != bg).sum()), int(br.sum()), int(bg.sum())]
+        d2 = (g.double() - r.double()).pow(2).sum(-1)
+        counts.append(row)
+        sums.append([float(d2.sum()), float(na), float(d2[heavy].sum()), float(heavy.sum())])
+        o += na
+    return torch.tensor(counts, dtype=torch.int64), torch.tensor(sums, dtype=torch.float64)

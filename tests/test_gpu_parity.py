@@ -509,3 +509,48 @@ def test_training_losses_with_cuda_denoiser(R):
     ref = diffusion.training_losses(ref_model, x0, t, dict(mask=mask), noise=noise)
     for k in ("mse", "vb", "loss"):
         assert torch.allclose(terms[k].cpu(), ref[k], rtol=1e-3, atol=1e-5), (k, terms[k], ref[k])
+
+
+# --------------------------------------------------------------------------------------- evaluation step
+@pytest.mark.parametrize("name", ["sample_qualities_exact", "sample_qualities_noisy"])
+def test_bond_graph_metrics_bit_exact_and_vs_reference_golden(R, name):
+    """cb2_eval_bond_graphs: the six integer counts per structure equal the oracle's exactly, the derived metrics equal what the
+    unmodified reference's eval_sample_qualities returned (golden)."""
+    from codlad_b200 import metrics
+    g = P.golden(name)
+    ref, gen = torch.from_numpy(g["xyz_ref"]), torch.from_numpy(g["xyz_gen"])
+    z, num = torch.from_numpy(g["z"].astype(np.int64)), g["num_atoms"].tolist()
+    counts, sums = metrics.bond_graph_stats(ref.cuda(), gen.cuda(), z.cuda(), num)
+    c_ref, s_ref = R.sample_quality_stats(ref, gen, z, num)
+    assert torch.equal(counts.cpu(), c_ref)
+    assert torch.allclose(sums.cpu(), s_ref, rtol=1e-12, atol=0)
+    q = metrics.eval_sample_qualities(ref.cuda(), gen.cuda(), z.cuda(), num)
+    want = g["q"]
+    assert (q["heavy_valid"].cpu().double().numpy() == want[:, 0]).all() and (q["all_valid"].cpu().double().numpy() == want[:, 1]).all()
+    np.testing.assert_allclose(q["heavy_graph_diff_ratio"].cpu().numpy(), want[:, 2], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(q["all_graph_diff_ratio"].cpu().numpy(), want[:, 3], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(q["all_rmsd"].cpu().numpy(), want[:, 4], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(q["heavy_rmsd"].cpu().numpy(), want[:, 5], rtol=1e-6, atol=1e-9)
+    lists = metrics.valid_ratio_and_cut_off_result(ref.cuda(), gen.cuda(), torch.tensor(num), z)
+    assert lists[0] == want[:, 0].tolist() and lists[1] == want[:, 1].tolist() and len(lists[2]) == len(num)
+
+
+def test_bond_graph_metrics_on_backmapped_ensemble(eng, R):
+    """The metric on what the path produces: a 120-residue protein backmapped 4 times (f16 tier), every member scored against
+    member 0 -- ragged structure sizes are exercised by mixing in a second protein; counts equal the oracle's exactly."""
+    from codlad_b200 import metrics, sampler
+    prots = [synthetic.make_protein(120, 1, seed=911), synthetic.make_protein(77, 1, seed=912)]
+    batch = synthetic.collate_many(prots)
+    fs = sampler.frames_from_batch(batch, [p.info for p in prots], 2)
+    bm = sampler.Backmapper(weights.init_denoiser_state(0), weights.init_vae_decode_state(0), "N6", num_sampling_steps=10, precision="f16")
+    out = bm.sample(bm.upload(fs), fs, generator=torch.Generator(device="cuda").manual_seed(3))
+    xyz = out["xyz"]
+    num = fs.num_atoms.repeat(2).tolist()                       # member order: ensemble-major (b = e * F + f)
+    first = xyz[:sum(num[:2])]
+    ref = torch.cat([first, first], 0)
+    z = torch.tensor([7, 6, 6, 8, 6, 6, 16, 8, 1], dtype=torch.int64).repeat(xyz.shape[0] // 9 + 1)[:xyz.shape[0]]
+    counts, sums = metrics.bond_graph_stats(ref, xyz, z.cuda(), num)
+    c_ref, s_ref = R.sample_quality_stats(ref.cpu(), xyz.cpu(), z, num)
+    assert torch.equal(counts.cpu(), c_ref)
+    assert torch.allclose(sums.cpu(), s_ref, rtol=1e-12, atol=0)
+    assert int(counts[0, 0]) == 0 and int(counts[1, 0]) == 0    # members 0 are scored against themselves

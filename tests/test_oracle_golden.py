@@ -98,3 +98,20 @@ def test_ic_to_xyz_large_angles():
     batch = synthetic.collate(prot)
     xyz = R.ic_to_xyz(batch["OG_CG_nxyz"].reshape(-1, L + 2, 4), torch.from_numpy(g["ic"]), prot.info)
     assert P.rmsd(xyz, g["xyz"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["sample_qualities_exact", "sample_qualities_noisy"])
+def test_sample_quality_stats_against_reference_golden(name):
+    """oracle.restate.sample_quality_stats vs eval_sample_qualities of the unmodified reference (valid flags, graph-difference
+    ratios, RMSDs) on stored all-atom structures."""
+    g = P.golden(name)
+    ref, gen = torch.from_numpy(g["xyz_ref"]), torch.from_numpy(g["xyz_gen"])
+    z, num = torch.from_numpy(g["z"].astype(np.int64)), g["num_atoms"].tolist()
+    counts, sums = R.sample_quality_stats(ref, gen, z, num)
+    q = g["q"]
+    c = counts.double()
+    assert ((counts[:, 3] == 0).double().numpy() == q[:, 0]).all() and ((counts[:, 0] == 0).double().numpy() == q[:, 1]).all()
+    np.testing.assert_allclose(((c[:, 4] - c[:, 5]).abs() / c[:, 4]).numpy(), q[:, 2], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(((c[:, 1] - c[:, 2]).abs() / c[:, 1]).numpy(), q[:, 3], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(torch.sqrt(sums[:, 0] / sums[:, 1]).numpy(), q[:, 4], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(torch.sqrt(sums[:, 2] / sums[:, 3]).numpy(), q[:, 5], rtol=1e-6, atol=1e-9)
