@@ -38,36 +38,6 @@ struct NodeTcParams {
     int trace_slot;              // debug: launch window slot (trace_window)
 };
 
-__device__ __forceinline__ void ldg_f32x8(const float* p, float* v) {
-    uint32_t r[8];
-    ldg256_coherent(p, r);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void stg_f32x8(float* p, const float* v) {
-    uint32_t r[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
-    stg256(p, r);
-}
-__device__ __forceinline__ void ld32(const float* p, float* v) {       // 32 consecutive floats, same address in every lane
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
-        v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-    }
-}
-// write 32 consecutive columns [c0, c0+32) of row r as fp16 into a swizzled K-major operand tile
-__device__ __forceinline__ void store_row_chunk(unsigned char* tile, int r, int c0, const float* v) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        uint32_t o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = f2_to_h2(v[u * 8 + e * 2], v[u * 8 + e * 2 + 1]);
-        *reinterpret_cast<uint4*>(tile + tile_off(r, (c0 >> 3) + u)) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-}
-
 constexpr int NODE_EPI_THREADS = 512;
 constexpr int NODE_CTA_THREADS = NODE_EPI_THREADS + 64;     // + MMA warp + TMA warp (one lane each)
 constexpr int NT = 32;                       // nodes per CTA = the N extent of every MMA
