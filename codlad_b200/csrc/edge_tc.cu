@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
         uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
-        uint32_t pcA[16], pcB[16];                                      // gathered halves, double buffered one stage ahead
+        uint32_t pcA[16];
         pdl_wait();                                                     // P16 / S / h_E belong to the previous kernels of the step
 
         // ENC_NODE / DEC: "E3" (read the reduced sums out of TMEM, store S, release the accumulator, fetch the slot's next
@@ -490,10 +490,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             };
 #pragma unroll 1
             for (int s2 = 0; s2 < NSLOT; s2 += 2) {
-                if (s2 < n) { if (s2 + 1 < n) { ld_pc(m1, pcB); prefetch_pa(m1); } epi1(s2, pcA); }
+                if (s2 < n) { if (s2 > 0) ld_pc(m0, pcA); if (s2 + 1 < n) prefetch_pa(m1); epi1(s2, pcA); }
                 if (MODE != EDGE_ENC_EDGE && s2 == 0 && pending3) { drain(3, t0 + 3); pending3 = false; }
                 rotate();
-                if (s2 + 1 < n) { if (s2 + 2 < n) { ld_pc(m1, pcA); prefetch_pa(m1); } epi1(s2 + 1, pcB); }
+                if (s2 + 1 < n) { ld_pc(m0, pcA); if (s2 + 2 < n) prefetch_pa(m1); epi1(s2 + 1, pcA); }
                 rotate();
             }
             ph ^= 1;
