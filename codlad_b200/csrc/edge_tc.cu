@@ -368,9 +368,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         };
         auto node0_of = [&](const TileMeta& m) { return meta_member(m) * p.L + meta_tin(m) * NPT; };
         auto nv_of = [&](const TileMeta& m) { return min(NPT, p.L - meta_tin(m) * NPT); };
-        auto prefetch_pa = [&](const TileMeta& m) {                     // pull the own-half segment of the next stage into L1
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P16 + (size_t)(node0_of(m) + (meta_row_valid(m) ? q_of_r : 0)) * 256 + c0));
-        };
         // neighbour-sum mask of this thread's row (reference: mask_attend = mask_i mask_j; the decoder passes no mask)
         auto row_keep = [&](const TileMeta& m) -> uint32_t {
             if (!meta_row_valid(m)) return 0u;
@@ -407,7 +404,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
         uint32_t ph_res = 0;                                            // parity of the residual re-load barriers (one phase per round)
-        uint32_t pcA[16];
         pdl_wait();                                                     // P16 / S / h_E belong to the previous kernels of the step
 
         // ENC_NODE / DEC: "E3" (read the reduced sums out of TMEM, store S, release the accumulator, fetch the slot's next
@@ -437,15 +433,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 
         for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride) {
             const int n = min(NSLOT, tile_end - t0);                    // live slots of this round
-            // gathered halves of the round's first tile: issued here, not at the bottom of the previous round, so that the
-            // compiler's scoreboard wait at the loop back-edge does not expose the gather latency (it now hides behind the
-            // first accumulator wait)
-            ld_pc(m0, pcA);
-            prefetch_pa(m0);
             // ================= E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile
-            auto epi1 = [&](int s, const uint32_t (&pc)[16]) {
+            auto epi1 = [&](int s) {
                 unsigned char* T = sT + s * TILE_BYTES;
-                uint32_t pa[16];
+                uint32_t pc[16];                                        // gathered half of this tile's rows (loaded here, not a stage ahead:
+                ld_pc(m0, pc);                                          //  the registers a prefetch holds cost more than its latency)
+                uint32_t pa[16];                                        // own half: two nodes per tile, L1-resident after the first warp
                 const __half* pa_src = p.P16 + (size_t)(node0_of(m0) + (meta_row_valid(m0) ? q_of_r : 0)) * 256 + c0;
                 ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
                 ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
@@ -489,11 +482,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 mark(3, s);
             };
 #pragma unroll 1
-            for (int s2 = 0; s2 < NSLOT; s2 += 2) {
-                if (s2 < n) { if (s2 > 0) ld_pc(m0, pcA); if (s2 + 1 < n) prefetch_pa(m1); epi1(s2, pcA); }
-                if (MODE != EDGE_ENC_EDGE && s2 == 0 && pending3) { drain(3, t0 + 3); pending3 = false; }
-                rotate();
-                if (s2 + 1 < n) { ld_pc(m0, pcA); if (s2 + 2 < n) prefetch_pa(m1); epi1(s2 + 1, pcA); }
+            for (int s = 0; s < NSLOT; ++s) {
+                if (s < n) epi1(s);
+                if (MODE != EDGE_ENC_EDGE && s == 0 && pending3) { drain(3, t0 + 3); pending3 = false; }
                 rotate();
             }
             ph ^= 1;
