@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         // (MMA and TMA issue are split because a thread's tcgen05.mma stalls behind its own in-flight bulk copies.)
         // Both warps run their control flow with all 32 lanes and issue through elect.sync (see elect_one()).
         auto T_u32 = [&](int g) { return smem_u32(sT + g * TILE_BYTES); };
-        // debug timeline of CTA 0's control warps (lane 0): MMA warp -> trace[5120..], TMA warp -> trace[5632..]
+#ifdef CB2_TRACE_CTRL                                                   // debug builds (scratch/build_variant.sh -DCB2_TRACE_CTRL): timeline of CTA 0's
+        // control warps (lane 0): MMA warp -> trace[5120..], TMA warp -> trace[5632..]
         unsigned long long* ctr = (p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0) ? p.trace + (tid >= EPI_THREADS + 32 ? 5632 : 5120) : nullptr;
         int n_ctr = 0;
         auto cmark = [&](int ev, int g) {
@@ -161,6 +162,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 ctr[0] = (unsigned long long)(++n_ctr);
             }
         };
+#else
+        auto cmark = [](int, int) {};
+#endif
         auto bar_load = [&](int g) { return smem_u32(&sBar[1 + 3 * g]); };
         auto bar_acc = [&](int g) { return smem_u32(&sBar[2 + 3 * g]); };
         auto bar_epi = [&](int g) { return smem_u32(&sBar[3 + 3 * g]); };
@@ -390,9 +394,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         };
 
-        unsigned long long* trace = (p.trace != nullptr && p.trace_epi && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
-        int n_trace = 0;
-        auto mark = [&](int ev, int s) {               // debug timeline (off unless the plan's "tc_trace" buffer was requested)
+#ifdef CB2_TRACE_EPI                                                    // epilogue timeline of CTA 0 / thread 0 (debug builds only: the marks
+        unsigned long long* trace = (p.trace != nullptr && p.trace_epi && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;      // cost registers and code
+        int n_trace = 0;                                                //  in every stage of the hot loop)
+        auto mark = [&](int ev, int s) {
             if (trace != nullptr && n_trace < 500) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -400,6 +405,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 trace[0] = (unsigned long long)(++n_trace);
             }
         };
+#else
+        auto mark = [](int, int) {};
+#endif
         TileMeta m0 = first_meta(tile_begin + 0), m1 = first_meta(tile_begin + 1), m2 = first_meta(tile_begin + 2), m3 = first_meta(tile_begin + 3);
         auto rotate = [&]() { const TileMeta t = m0; m0 = m1; m1 = m2; m2 = m3; m3 = t; };
         uint32_t ph = 0;                                                // parity of the acc barriers (all slots advance in lock step)
