@@ -475,6 +475,14 @@ int cb2_plan_set_frames(cb2_plan* h, const float* X, const int* lengths, const i
     CB2_CUDA(cudaMemcpyAsync(p.cg_z, cg_z, (size_t)p.F * p.L * sizeof(int), cudaMemcpyDeviceToDevice, s));
     CB2_CUDA(cudaMemcpyAsync(p.frame_of, frame_of, p.NB * sizeof(int), cudaMemcpyDeviceToDevice, s));
     if (p.model == nullptr) { h->frames_ready = true; return 0; }      // decode-only plan
+    {   // host-side knowledge of the geometry: are there padded residues at all?  (lets the tensor-core message kernels skip
+        // the neighbour mask when every frame is full length; once per frame set, not on the step path)
+        std::vector<int> len((size_t)p.F);
+        CB2_CUDA(cudaMemcpyAsync(len.data(), p.lengths, (size_t)p.F * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CB2_CUDA(cudaStreamSynchronize(s));
+        p.all_full = true;
+        for (int f = 0; f < p.F; ++f) p.all_full = p.all_full && len[f] >= p.L;
+    }
     if (int e = launch_knn(p.X, p.lengths, p.F, p.L, p.K, p.nbr_dist, p.nbr_idx, s)) return e;
     if (int e = launch_edge_features(*p.model, p.X, p.lengths, p.nbr_idx, p.nbr_dist, p.F, p.L, p.K, p.E_dbg, p.hE0, p.precision, s)) return e;
     p.launches += 2;

@@ -46,6 +46,7 @@ struct TcParams {
     int L, K, NPT, tiles_per_member, n_tiles;
     int in_is_frame;                 // layer 0 of the encoder reads h_E0 (indexed by frame)
     int single_frame;                // F == 1: every member uses frame 0 (no frame_of lookup on the metadata path)
+    int mask_rows;                   // ENC_NODE / DEC: some rows must be zeroed before the reduction (padding, neighbour mask, partial tiles)
     int w_row[3];                    // first row of each weight block in the packed weight tensor
     int n_w;                         // 2 (ENC_NODE / DEC) or 3 (ENC_EDGE)
     const __half* P16;               // [N, 256] fp16: [own half Wa h_V_i + b1 | gathered half Wc h_V_j (+ decoder table)]
@@ -501,7 +502,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             for (int s = 0; s < NSLOT; ++s) {
                 if (s < n) {
                     unsigned char* T = sT + s * TILE_BYTES;
-                    const uint32_t keep = MODE == EDGE_ENC_EDGE ? 0xffffffffu : row_keep(m0);
+                    // rows outside the neighbour sum (padded residues, masked neighbours, the unused rows of a partial tile) are zeroed;
+                    // when the geometry has none of them (full-length frames, NPT K = 128) the whole step is skipped
+                    const bool masked = MODE != EDGE_ENC_EDGE && p.mask_rows;
+                    const uint32_t keep = masked ? row_keep(m0) : 0xffffffffu;
                     uint32_t bb[16];
                     ldg256(p.b2h + c0, *reinterpret_cast<uint32_t(*)[8]>(&bb[0]));
                     ldg256(p.b2h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&bb[8]));
@@ -526,7 +530,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const __half2 x = __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(bb[g16 * 8 + e]));
-                            o[e] = as_u32(gelu2_h2(x)) & keep;
+                            o[e] = as_u32(gelu2_h2(x));
+                        }
+                        if (masked) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] &= keep;
                         }
 #ifdef CB2_X_NOSTS
                         if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, g16, o);
@@ -685,6 +693,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     const bool first = (layer == 0 && mode != EDGE_DEC);
     tp.in_is_frame = first ? 1 : 0;
     tp.single_frame = p.F == 1 ? 1 : 0;
+    tp.mask_rows = (tp.NPT * p.K < 128 || p.L % tp.NPT != 0 || (mode != EDGE_DEC && !p.all_full)) ? 1 : 0;
     auto row_of = [&](const __half* w) { return (int)((w - m.dev_f16) / 128); };
     if (mode == EDGE_ENC_NODE) {
         const EncLayerW& e = m.enc[layer];

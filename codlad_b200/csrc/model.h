@@ -74,6 +74,7 @@ struct Plan {
     __half* P16[2] = {nullptr, nullptr};    // fp16 tier: [NB*L, 256] = [own half + bias | gathered half] of the two first-layer splits
     __half* mod16 = nullptr;                // fp16 tier: [mod_capacity, 3, 256] edge-stream adaLN: gate (1 + scale) | gate * shift
     int num_sms = 148;
+    bool all_full = false;                    // every frame has L residues (no padding, hence no neighbour mask)
     unsigned long long* tc_trace = nullptr;   // debug: stage timestamps of one tensor-core edge pipeline ("tc_trace" buffer)
     float* silu_c = nullptr;        // [mod_capacity, 128] scratch of the timestep embedder
     float* S = nullptr;             // [NB*L, 128]  aggregated messages
