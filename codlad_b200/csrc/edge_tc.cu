@@ -603,9 +603,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         const float tsum = (part[0] + part[2]) + (part[4] + part[6]), tsq = (part[1] + part[3]) + (part[5] + part[7]);
                         const float mean = tsum * (1.0f / 128.0f);
                         const float rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
-                        const __half2 rstd2 = __float2half2_rn(rstd), mean2 = __float2half2_rn(mean);
+                        const __half2 rstd2 = __float2half2_rn(rstd), nmr2 = __float2half2_rn(-mean * rstd);
                         const __half* mod_row = p.mod16 + (size_t)bmem * p.mod16_stride + c0;
-                        // pass B (packed half): out = (v - mean) * (rstd * A[c]) + B[c],  A = gate (1 + scale), B = gate * shift
+                        // pass B (packed half): out = (v rstd - mean rstd) A[c] + B[c],  A = gate (1 + scale), B = gate * shift
 #pragma unroll
                         for (int c16 = 0; c16 < 4; ++c16) {
                             uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16));
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                o[e] = as_u32(__hfma2(__hsub2(as_h2(v4[e]), mean2), __hmul2(rstd2, as_h2(a4[e])), as_h2(b4[e])));
+                                o[e] = as_u32(__hfma2(__hfma2(as_h2(v4[e]), rstd2, nmr2), as_h2(a4[e]), as_h2(b4[e])));
                             *slot = make_uint4(o[0], o[1], o[2], o[3]);
                         }
                         stage_done(s, true);                             // tile complete: the TMA lane stores it and reloads the slot
