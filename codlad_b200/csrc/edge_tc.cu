@@ -67,7 +67,8 @@ constexpr int EPI_THREADS = 512;                // thread (row r, column quarter
 constexpr int CTA_THREADS = EPI_THREADS + 64;   // + two control warps (one lane each): MMA issue, TMA issue
 constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 KB operand buffer + 128 TMEM columns each)
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the epilogue threads only
+// the four warps that hold the column quarters of the same 32 rows (row quarter q): named barrier 1 + q, 128 threads
+__device__ __forceinline__ void row_quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
 // per-thread view of a tile, packed into two registers (four of them are live; they rotate so that the stage code
 // exists once):  a = member << 16 | tile-within-member (advanced without divisions) ;  b = member-local neighbour index j
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         // summed in a fixed order, so the result is deterministic
                         tmem_st2(tmem_lane + (uint32_t)(s * 128), sum, sq);
                         tc_fence_before();
-                        epi_sync();
+                        row_quarter_sync(quarter);
                         tc_fence_after();
                         float part[8];
                         tmem_ld2_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128), 32u, part);
