@@ -69,7 +69,8 @@ __device__ __forceinline__ int weight_rows(const NodeTcParams& p, int* rows) {
     return n;
 }
 
-constexpr size_t NODE_TC_SMEM = (size_t)N_SLOT * TILE_BYTES + (size_t)N_ACT * ACT_BYTES + 2 * 4 * 4 * 16 * 4 + 4 * NT * 4 + 12 * 8 + 16;
+constexpr int N_BAR = 20;                    // mbarriers of one node block (see node_block)
+constexpr size_t NODE_TC_SMEM = (size_t)N_SLOT * TILE_BYTES + (size_t)N_ACT * ACT_BYTES + 2 * 4 * 4 * 16 * 4 + 4 * NT * 4 + N_BAR * 8 + 16;
 
 // One block of NT nodes [node0, min(node0 + NT, n_end)) through the whole node update.  Called by every thread of a 576-thread CTA
 // (16 epilogue warps, MMA warp 16, TMA warp 17) with `smem` = the CTA's dynamic shared memory (NODE_TC_SMEM bytes, 1024-aligned,
@@ -84,15 +85,19 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
     float* sMk = reinterpret_cast<float*>(sB + NT);                    //           node mask
     float* sCnt = sMk + NT;                                            //           masked-neighbour count
     int* sZ = reinterpret_cast<int*>(sCnt + NT);                       //           residue type
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(sZ + NT);             // [0..4] slot full, [5..9] slot free, [10] MMAs done, [11] operands ready
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(sZ + NT);             // [0..4] slot full, [5..9] slot free, [10] MMAs done, [11] operands ready,
+                                                                       // [12..15] FFN-in chunk c accumulated, [16..19] FFN hidden chunk c written
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto bar_full = [&](int s) { return smem_u32(&sBar[s]); };
     auto bar_free = [&](int s) { return smem_u32(&sBar[N_SLOT + s]); };
     const uint32_t bar_mma = smem_u32(&sBar[10]), bar_act = smem_u32(&sBar[11]);
+    auto bar_chunk = [&](int c) { return smem_u32(&sBar[12 + c]); };
+    auto bar_mid = [&](int c) { return smem_u32(&sBar[16 + c]); };
     if (tid == 0) {
         for (int s = 0; s < N_SLOT; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_free(s), 1); }
         mbar_init(bar_mma, 1); mbar_init(bar_act, NODE_EPI_THREADS / 32);
+        for (int c = 0; c < 4; ++c) { mbar_init(bar_chunk(c), 1); mbar_init(bar_mid(c), NODE_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < NT) {
@@ -138,6 +143,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
         } else if (warp == 16) {
             // ------------------------------------------------------------------ MMA lane: D[feature, node] = W[feature, :] . act[node, :]
             // (the whole warp runs the control flow; the instructions are issued by an elected lane)
+#ifdef CB2_TRACE_CTRL                                                   // debug builds only (scratch/build_variant.sh -DCB2_TRACE_CTRL)
             unsigned long long* ctrace = (p.trace != nullptr && blockIdx.x == 0 && lane == 0) ? p.trace + 512 : nullptr;
             int n_ct = 0;
             auto cmark = [&](int ev) {
@@ -148,6 +154,9 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                     ctrace[0] = (unsigned long long)(++n_ct);
                 }
             };
+#else
+            auto cmark = [](int) {};
+#endif
             cmark(0);
             uint32_t ph_act = 0;
             int ti = 0;
@@ -171,8 +180,12 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
             auto wait_act = [&]() { mbar_wait(bar_act, ph_act); ph_act ^= 1; tc_fence_after(); cmark(2); };
             if (p.do_update) {
                 wait_act(); gemm(0, R1, false); commit_phase();
-                wait_act(); for (int c = 0; c < 4; ++c) gemm(1, R2 + c * NT, false); commit_phase();
-                wait_act(); for (int c = 0; c < 4; ++c) gemm(2 + c, R3, c > 0); commit_phase();
+                // FFN: the four 128-feature chunks flow through chunk by chunk -- chunk c's GELU epilogue starts when its own GEMM has
+                // completed, and its share of the output GEMM when its hidden tile is written (no phase-wide hand-offs)
+                wait_act();
+                for (int c = 0; c < 4; ++c) { gemm(1, R2 + c * NT, false); if (elect_one()) umma_commit(bar_chunk(c)); __syncwarp(); }
+                for (int c = 0; c < 4; ++c) { mbar_wait(bar_mid(c), 0); tc_fence_after(); gemm(2 + c, R3, c > 0); }
+                commit_phase();
             }
             if (p.n_proj > 0) {
                 wait_act();
@@ -319,9 +332,10 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                 float bi[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) bi[c] = __ldg(p.bin + c * 128 + fl);
-                wait_mma();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    mbar_wait(bar_chunk(c), 0);
+                    tc_fence_after();
                     float acc[8];
                     tmem_ld8(tmem_lane + (uint32_t)(R2 + c * NT), acc);
                     unsigned char* dst = act_tile(2 + c);
@@ -331,9 +345,10 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                         sts_h(dst + act_off(nl0 + 2 * j, fl), __low2half(g));
                         sts_h(dst + act_off(nl0 + 2 * j + 1, fl), __high2half(g));
                     }
+                    fence_async_smem(); tc_fence_before(); __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_mid(c));
                 }
             }
-            publish();
             // ---- EB: h2 = mask * gate2 * (LN(h1 + acc + b_out) (1 + scale2) + shift2) ----
             {
                 const float bo = __ldg(p.bout + fl);
@@ -450,7 +465,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
     tc_fence_before();
     __syncthreads();
     if (tid == 0)                                     // the shared memory (and these barrier words) may be re-used by the caller
-        for (int i = 0; i < 12; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sBar[i])) : "memory");
+        for (int i = 0; i < N_BAR; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sBar[i])) : "memory");
     __syncthreads();
 }
 
