@@ -51,6 +51,8 @@ constexpr int R1 = 0, R2 = NT, R3 = 5 * NT;  // TMEM column regions: W3 output |
 static_assert(NT == 32, "the LayerNorm transpose-reduce below is written for 8 nodes per thread");
 
 __device__ __forceinline__ void node_epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// the four warps (feature quarters) that share a node group: named barrier 2 + group, 128 threads
+__device__ __forceinline__ void node_group_sync(int cq) { asm volatile("bar.sync %0, 128;" ::"r"(cq + 2) : "memory"); }
 
 // byte offset of (node r, feature f) inside an activation tile
 __device__ __forceinline__ uint32_t act_off(int r, int f) {
@@ -236,7 +238,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
             const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
             float* red = sRed + ((red_use & 1) * 16 + cq * 4) * 16;
             if ((lane & 1) == 0) red[quarter * 16 + idx] = q[0];
-            node_epi_sync();
+            node_group_sync(cq);
             float tot[16];
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
