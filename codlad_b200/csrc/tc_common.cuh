@@ -39,18 +39,27 @@ static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, 
     }
     if (final) __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // A waiting warp must not eat the issue slots of the warps doing arithmetic on the same scheduler: back off with
-    // nanosleep between probes.  The probe count is bounded so a protocol bug traps instead of hanging the GPU.
-    uint32_t done = 0, spins = 0;
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+// Slow path of a wait, kept out of line so that the polling loop, its back-off and the time-out bookkeeping are not replicated
+// (and do not hold registers) at every wait of the stage loops.  A waiting warp must not eat the issue slots of the warps doing
+// arithmetic on the same scheduler: back off with nanosleep between probes.  The probe count is bounded so that a protocol bug
+// traps instead of hanging the GPU.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
         __nanosleep(64);
+        if (mbar_try(bar, parity)) return;
         if (++spins == SPIN_LIMIT) mbar_timeout(bar, parity, false);      // (debug record; keeps waiting so that the other stuck warps record too)
         if (spins > SPIN_LIMIT + (SPIN_LIMIT >> 1)) mbar_timeout(bar, parity, true);
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
