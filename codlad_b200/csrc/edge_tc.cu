@@ -571,26 +571,24 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                             const uint4 t4 = *reinterpret_cast<const uint4*>(T + tile_off(r, (c0 >> 3) + c16));
                             rs[c16 * 4] = t4.x; rs[c16 * 4 + 1] = t4.y; rs[c16 * 4 + 2] = t4.z; rs[c16 * 4 + 3] = t4.w;
                         }
-                        // pass A: v = residual + (acc + b13) in packed half (v is parked as fp16 in the tile anyway), row statistics of
-                        // the parked values accumulated in fp32
+                        // pass A: v = residual + (acc + b13) in packed half, kept in registers; row statistics of those values in fp32
                         uint32_t b3r[16];
                         ldg256(p.b3h + c0, *reinterpret_cast<uint32_t(*)[8]>(&b3r[0]));
                         ldg256(p.b3h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&b3r[8]));
                         float sum = 0.f, sq = 0.f;
+                        uint32_t v16[16];
 #pragma unroll
                         for (int g16 = 0; g16 < 2; ++g16) {
                             float acc[16];
                             tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
-                            uint32_t o[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const __half2 v = __hadd2(as_h2(rs[g16 * 8 + e]), __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(b3r[g16 * 8 + e])));
                                 const float2 vf = __half22float2(v);
                                 sum += vf.x + vf.y;
                                 sq = fmaf(vf.x, vf.x, fmaf(vf.y, vf.y, sq));
-                                o[e] = as_u32(v);
+                                v16[g16 * 8 + e] = as_u32(v);
                             }
-                            st16(T, g16, o);
                         }
                         // row statistics: the four column quarters of a row exchange their partial sums through accumulator
                         // columns this thread has already drained (its own first two) -- tcgen05.st, one barrier, tcgen05.ld;
@@ -609,16 +607,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         // pass B (packed half): out = (v rstd - mean rstd) A[c] + B[c],  A = gate (1 + scale), B = gate * shift
 #pragma unroll
                         for (int c16 = 0; c16 < 4; ++c16) {
-                            uint4* slot = reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16));
-                            const uint4 vv = *slot;
                             const uint4 av = __ldg(reinterpret_cast<const uint4*>(mod_row + c16 * 8));
                             const uint4 bv = __ldg(reinterpret_cast<const uint4*>(mod_row + 128 + c16 * 8));
-                            const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w}, a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                            const uint32_t a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
                             uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                o[e] = as_u32(__hfma2(__hfma2(as_h2(v4[e]), rstd2, nmr2), as_h2(a4[e]), as_h2(b4[e])));
-                            *slot = make_uint4(o[0], o[1], o[2], o[3]);
+                                o[e] = as_u32(__hfma2(__hfma2(as_h2(v16[c16 * 4 + e]), rstd2, nmr2), as_h2(a4[e]), as_h2(b4[e])));
+                            *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16)) = make_uint4(o[0], o[1], o[2], o[3]);
                         }
                         stage_done(s, true);                             // tile complete: the TMA lane stores it and reloads the slot
                         mark(9, s);
