@@ -422,13 +422,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         auto drain = [&](int s, int next_tile) {
             const TileMeta m = m3;
             m3 = next_meta(m, next_tile);
-            if (cq == 0) {                                               // one warp per scheduler; the other twelve run ahead into the next stage
+            if (cq == s) {                                               // slot s is drained by column group s (one warp per scheduler): the four
+                                                                         // groups share the drains, the other twelve warps run ahead
                 mark(8, s);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph ^ 1);           // third commit of the tile (reduction MMA)
                 tc_fence_after();
                 mark(9, s);
                 float s4[4];
-                tmem_ld4(tmem_lane + (uint32_t)(s * 128), s4);          // lane = output column, 4 columns = nodes of the tile
+                tmem_ld4(tmem_lane - (uint32_t)c0 + (uint32_t)(s * 128), s4);     // lane = output column, 4 columns = nodes of the tile
                 const int nv = nv_of(m), node0 = node0_of(m);
 #pragma unroll
                 for (int q = 0; q < MAX_NPT; ++q)
@@ -453,12 +454,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
                 ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
                 mark(0, s);
-                // The warps that do not drain (cq != 0) never wait for the slot's third commit (the reduction MMA), and the phases
+                // The warps that do not drain slot s (cq != s) never wait for the slot's third commit (the reduction MMA), and the phases
                 // on either side of it have the same parity: a warp that ran a whole E2 phase ahead of a straggler would sail
                 // through the accumulator wait below on the stale "MMA 2 complete" state (seen as a rare dead-lock on large
                 // working sets, where TLB misses skew the warps).  The slot's "drained" barrier advances once per round and
                 // only after the reduction has completed, so it orders them exactly.
-                if (MODE != EDGE_ENC_EDGE && cq != 0 && t0 != tile_begin) mbar_wait(smem_u32(&sBar[25 + s]), ph ^ 1);
+                if (MODE != EDGE_ENC_EDGE && cq != s && t0 != tile_begin) mbar_wait(smem_u32(&sBar[25 + s]), ph ^ 1);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                 tc_fence_after();
                 mark(1, s);
