@@ -46,7 +46,6 @@ struct TcParams {
     int L, K, NPT, tiles_per_member, n_tiles;
     int in_is_frame;                 // layer 0 of the encoder reads h_E0 (indexed by frame)
     int single_frame;                // F == 1: every member uses frame 0 (no frame_of lookup on the metadata path)
-    int mask_rows;                   // ENC_NODE / DEC: some rows must be zeroed before the reduction (padding, neighbour mask, partial tiles)
     int w_row[3];                    // first row of each weight block in the packed weight tensor
     int n_w;                         // 2 (ENC_NODE / DEC) or 3 (ENC_EDGE)
     const __half* P16;               // [N, 256] fp16: [own half Wa h_V_i + b1 | gathered half Wc h_V_j (+ decoder table)]
@@ -79,7 +78,9 @@ __device__ __forceinline__ int meta_tin(const TileMeta& m) { return (int)(m.a & 
 __device__ __forceinline__ int meta_j(const TileMeta& m) { return (int)(m.b & 0x7fffffffu); }
 __device__ __forceinline__ bool meta_row_valid(const TileMeta& m) { return (int)m.b >= 0; }
 
-template <int MODE>
+// MASKED (ENC_NODE / DEC): some rows must be zeroed before the reduction (padded residues, masked neighbours, the unused rows of
+// a partial tile).  A template parameter, not a run-time flag: the unmasked build has no trace of the masking in its stage loop.
+template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int N_W = MODE == EDGE_ENC_EDGE ? 3 : 2;
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     unsigned char* T = sT + s * TILE_BYTES;
                     // rows outside the neighbour sum (padded residues, masked neighbours, the unused rows of a partial tile) are zeroed;
                     // when the geometry has none of them (full-length frames, NPT K = 128) the whole step is skipped
-                    const bool masked = MODE != EDGE_ENC_EDGE && p.mask_rows;
+                    constexpr bool masked = MODE != EDGE_ENC_EDGE && MASKED;
                     const uint32_t keep = masked ? row_keep(m0) : 0xffffffffu;
                     uint32_t bb[16];
                     ldg256(p.b2h + c0, *reinterpret_cast<uint32_t(*)[8]>(&bb[0]));
@@ -664,9 +665,11 @@ int edge_tc_prepare(Plan& p) {
     int dev = 0;
     CB2_CUDA(cudaGetDevice(&dev));
     CB2_CUDA(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_NODE)));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_DEC)));
-    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_EDGE)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_NODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_NODE)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_NODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_NODE)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_DEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_DEC)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_DEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_DEC)));
+    CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_EDGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_EDGE)));
     return 0;
 }
 
@@ -691,7 +694,7 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
     const bool first = (layer == 0 && mode != EDGE_DEC);
     tp.in_is_frame = first ? 1 : 0;
     tp.single_frame = p.F == 1 ? 1 : 0;
-    tp.mask_rows = (tp.NPT * p.K < 128 || p.L % tp.NPT != 0 || (mode != EDGE_DEC && !p.all_full)) ? 1 : 0;
+    const bool masked = tp.NPT * p.K < 128 || p.L % tp.NPT != 0 || (mode != EDGE_DEC && !p.all_full);
     auto row_of = [&](const __half* w) { return (int)((w - m.dev_f16) / 128); };
     if (mode == EDGE_ENC_NODE) {
         const EncLayerW& e = m.enc[layer];
@@ -712,9 +715,13 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
         tp.w_row[0] = row_of(d.W1b2_h); tp.w_row[1] = row_of(d.W2_h); tp.b2h = d.b2_16;
     }
     const int grid = min(p.num_sms, tp.n_tiles);
-    if (mode == EDGE_ENC_NODE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_NODE>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
-    else if (mode == EDGE_ENC_EDGE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_EDGE>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
-    else CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_DEC>, dim3(grid), dim3(CTA_THREADS), tc_smem_bytes(mode), s, maps, tp));
+    const dim3 g(grid), b(CTA_THREADS);
+    const size_t sm = tc_smem_bytes(mode);
+    if (mode == EDGE_ENC_EDGE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_EDGE, false>, g, b, sm, s, maps, tp));
+    else if (mode == EDGE_ENC_NODE && masked) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_NODE, true>, g, b, sm, s, maps, tp));
+    else if (mode == EDGE_ENC_NODE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_NODE, false>, g, b, sm, s, maps, tp));
+    else if (masked) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_DEC, true>, g, b, sm, s, maps, tp));
+    else CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_DEC, false>, g, b, sm, s, maps, tp));
     CB2_LAUNCH_CHECK();
     p.launches++;
     return 0;
