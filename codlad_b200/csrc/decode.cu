@@ -29,46 +29,62 @@ __global__ void codebook_norms_kernel(const float* __restrict__ cb, int M, float
     e2[m] = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
 }
 
-__global__ void __launch_bounds__(128) vq_lookup_kernel(const float* __restrict__ x, int N, int L, const int* __restrict__ lengths,
-                                                        const int* __restrict__ frame_of, const float* __restrict__ mean,
-                                                        const float* __restrict__ stdv, int denorm, const float* __restrict__ cb,
-                                                        const float* __restrict__ e2, int M, const float* __restrict__ mapw_t,
-                                                        const float* __restrict__ mapb, int* __restrict__ idx_out,
-                                                        float* __restrict__ zq_out, float* __restrict__ S40) {
+constexpr int VQ_WARPS = 8;         // warps per CTA
+constexpr int VQ_PER_WARP = 4;      // residues per warp (the codebook is staged once per CTA for 32 residues)
+
+// One warp per residue: lanes stride the codes (each lane keeps the first minimum of its own increasing subsequence), then a
+// lexicographic (distance, index) minimum across the lanes -- the index of the first minimum, exactly what a sequential scan
+// (and the reference's argmax over -dist) returns.  The distance arithmetic per code is unchanged.
+__global__ void __launch_bounds__(VQ_WARPS * 32) vq_lookup_kernel(const float* __restrict__ x, int N, int L, const int* __restrict__ lengths,
+                                                                  const int* __restrict__ frame_of, const float* __restrict__ mean,
+                                                                  const float* __restrict__ stdv, int denorm, const float* __restrict__ cb,
+                                                                  const float* __restrict__ e2, int M, const float* __restrict__ mapw_t,
+                                                                  const float* __restrict__ mapb, int* __restrict__ idx_out,
+                                                                  float* __restrict__ zq_out, float* __restrict__ S40) {
     extern __shared__ __align__(16) float smem[];
     float* sCb = smem;            // [M*3]
     float* sE2 = smem + M * 3;    // [M]
     for (int t = threadIdx.x; t < M * 3; t += blockDim.x) sCb[t] = cb[t];
     for (int t = threadIdx.x; t < M; t += blockDim.x) sE2[t] = e2[t];
     __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float v0 = x[n * 3], v1 = x[n * 3 + 1], v2 = x[n * 3 + 2];
-    if (denorm) {   // feature * std + mean, two roundings like the reference's torch ops
-        v0 = __fadd_rn(__fmul_rn(v0, stdv[0]), mean[0]);
-        v1 = __fadd_rn(__fmul_rn(v1, stdv[1]), mean[1]);
-        v2 = __fadd_rn(__fmul_rn(v2, stdv[2]), mean[2]);
-    }
-    const int b = n / L, i = n - b * L;
-    const bool valid = i < lengths[frame_of[b]];
-    int best = -1;
-    float q0 = v0, q1 = v1, q2 = v2;
-    if (valid) {
-        const float x2 = __fadd_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), __fmul_rn(v2, v2));
-        float bestd = 0.f;
-        for (int m = 0; m < M; ++m) {
-            const float dotp = __fadd_rn(__fadd_rn(__fmul_rn(v0, sCb[m * 3]), __fmul_rn(v1, sCb[m * 3 + 1])), __fmul_rn(v2, sCb[m * 3 + 2]));
-            const float s = __fadd_rn(__fadd_rn(x2, sE2[m]), __fmul_rn(dotp, -2.0f));
-            const float d = __fsqrt_rn(fmaxf(s, 0.0f));
-            if (best < 0 || d < bestd) { best = m; bestd = d; }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = 0; k < VQ_PER_WARP; ++k) {
+        const int n = (blockIdx.x * VQ_WARPS + warp) * VQ_PER_WARP + k;
+        if (n >= N) return;
+        float v0 = x[n * 3], v1 = x[n * 3 + 1], v2 = x[n * 3 + 2];
+        if (denorm) {   // feature * std + mean, two roundings like the reference's torch ops
+            v0 = __fadd_rn(__fmul_rn(v0, stdv[0]), mean[0]);
+            v1 = __fadd_rn(__fmul_rn(v1, stdv[1]), mean[1]);
+            v2 = __fadd_rn(__fmul_rn(v2, stdv[2]), mean[2]);
         }
-        q0 = sCb[best * 3]; q1 = sCb[best * 3 + 1]; q2 = sCb[best * 3 + 2];
-    }
-    idx_out[n] = best;
-    zq_out[n * 3] = q0; zq_out[n * 3 + 1] = q1; zq_out[n * 3 + 2] = q2;
-    if (S40 != nullptr) {   // map_out: Linear(3 -> 36); columns 36..39 (residue embedding) are filled by the decoder
-        for (int o = 0; o < 36; ++o)
-            S40[(size_t)n * 40 + o] = fmaf(q2, mapw_t[2 * 36 + o], fmaf(q1, mapw_t[36 + o], fmaf(q0, mapw_t[o], mapb[o])));
+        const int b = n / L, i = n - b * L;
+        const bool valid = i < lengths[frame_of[b]];
+        int best = -1;
+        float q0 = v0, q1 = v1, q2 = v2;
+        if (valid) {            // (warp-uniform: every lane works on the same residue)
+            const float x2 = __fadd_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), __fmul_rn(v2, v2));
+            float bestd = 0.f;
+            for (int m = lane; m < M; m += 32) {
+                const float dotp = __fadd_rn(__fadd_rn(__fmul_rn(v0, sCb[m * 3]), __fmul_rn(v1, sCb[m * 3 + 1])), __fmul_rn(v2, sCb[m * 3 + 2]));
+                const float s = __fadd_rn(__fadd_rn(x2, sE2[m]), __fmul_rn(dotp, -2.0f));
+                const float d = __fsqrt_rn(fmaxf(s, 0.0f));
+                if (best < 0 || d < bestd) { best = m; bestd = d; }
+            }
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bestd, off);
+                const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+                if (ob >= 0 && (best < 0 || od < bestd || (od == bestd && ob < best))) { best = ob; bestd = od; }
+            }
+            q0 = sCb[best * 3]; q1 = sCb[best * 3 + 1]; q2 = sCb[best * 3 + 2];
+        }
+        if (lane == 0) {
+            idx_out[n] = best;
+            zq_out[n * 3] = q0; zq_out[n * 3 + 1] = q1; zq_out[n * 3 + 2] = q2;
+        }
+        if (S40 != nullptr) {   // map_out: Linear(3 -> 36); columns 36..39 (residue embedding) are filled by the decoder
+            for (int o = lane; o < 36; o += 32)
+                S40[(size_t)n * 40 + o] = fmaf(q2, mapw_t[2 * 36 + o], fmaf(q1, mapw_t[36 + o], fmaf(q0, mapw_t[o], mapb[o])));
+        }
     }
 }
 
@@ -81,25 +97,30 @@ __global__ void __launch_bounds__(128) ic_edge_filter_kernel(const float* __rest
                                                              const float* __restrict__ Wd_t /* [4][15][40] */,
                                                              const float* __restrict__ bd /* [4][40] */, float cutoff,
                                                              float* __restrict__ w /* [4][E][40] */) {
-    // one warp per source row (frame node), lanes stride the 4*40 outputs of each edge
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n_rows) return;
-    const int f = warp / L;
+    // one CTA per source row (frame node); its warps stride the row's edges.  Per edge the 15 sinc basis functions and the cosine
+    // envelope are evaluated once (lane q < 15: basis q, lane 15: envelope) and broadcast; the lanes then stride the 4 x 40 outputs.
+    const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const int f = row / L;
     const float* Xf = X + (size_t)f * L * 3;
-    const int i = warp - f * L;
+    const int i = row - f * L;
     const float xi = Xf[i * 3], yi = Xf[i * 3 + 1], zi = Xf[i * 3 + 2];
-    for (int e = row_ptr[warp]; e < row_ptr[warp + 1]; ++e) {
+    const float kPi = 3.14159265358979323846f;
+    for (int e = row_ptr[row] + warp; e < row_ptr[row + 1]; e += blockDim.x >> 5) {
         const int j = col[e];
         const float dx = Xf[j * 3] - xi, dy = Xf[j * 3 + 1] - yi, dz = Xf[j * 3 + 2] - zi;
         const float dist = sqrtf(((dx * dx + 1e-8f) + (dy * dy + 1e-8f)) + (dz * dz + 1e-8f));   // preprocess_r, gcn_nn.py:66-70
-        float rbf[15];
-        const float kPi = 3.14159265358979323846f;
-#pragma unroll
-        for (int q = 0; q < 15; ++q) {
-            const float coef = (float)(q + 1) * kPi / cutoff;
-            rbf[q] = dist >= cutoff ? 0.f : (dist == 0.f ? coef : sinf(coef * dist) / dist);
+        float mine = 0.f;
+        if (lane < 15) {
+            const float coef = (float)(lane + 1) * kPi / cutoff;
+            mine = dist >= cutoff ? 0.f : (dist == 0.f ? coef : sinf(coef * dist) / dist);
+        } else if (lane == 15) {
+            mine = dist >= cutoff ? 0.f : 0.5f * (cosf(kPi * dist / cutoff) + 1.0f);
         }
-        const float env = dist >= cutoff ? 0.f : 0.5f * (cosf(kPi * dist / cutoff) + 1.0f);
+        float rbf[15];
+#pragma unroll
+        for (int q = 0; q < 15; ++q) rbf[q] = __shfl_sync(0xffffffffu, mine, q);
+        const float env = __shfl_sync(0xffffffffu, mine, 15);
         for (int t = lane; t < 160; t += 32) {
             const int blk = t / 40, c = t - blk * 40;
             float a = bd[blk * 40 + c];
@@ -335,7 +356,8 @@ int launch_vq_lookup(const VaeModel& v, const float* x, int N, int L, const int*
     const size_t smem = (size_t)v.M * 16;
     if (smem > 200 * 1024) { set_error("vq: codebook of %d entries does not fit shared memory", v.M); return (int)cudaErrorInvalidValue; }
     CB2_CUDA(cudaFuncSetAttribute(vq_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vq_lookup_kernel<<<(N + 127) / 128, 128, smem, s>>>(x, N, L, lengths, frame_of, v.mean, v.stdv, denorm, v.codebook, v.e2, v.M,
+    const int per_cta = VQ_WARPS * VQ_PER_WARP;
+    vq_lookup_kernel<<<(N + per_cta - 1) / per_cta, VQ_WARPS * 32, smem, s>>>(x, N, L, lengths, frame_of, v.mean, v.stdv, denorm, v.codebook, v.e2, v.M,
                                                         v.mapw_t, v.mapb, idx_out, zq_out, S40);
     CB2_LAUNCH_CHECK();
     return 0;
@@ -345,7 +367,7 @@ int launch_ic_edge_filters(const VaeModel& v, const float* X, int F, int L, cons
                            cudaStream_t s) {
     const int rows = F * L;
     if (E == 0) return 0;
-    ic_edge_filter_kernel<<<(rows * 32 + 127) / 128, 128, 0, s>>>(X, L, row_ptr, col, rows, E, v.Wd_t, v.bd, v.cutoff, w);
+    ic_edge_filter_kernel<<<rows, 128, 0, s>>>(X, L, row_ptr, col, rows, E, v.Wd_t, v.bd, v.cutoff, w);
     CB2_LAUNCH_CHECK();
     return 0;
 }
