@@ -374,14 +374,18 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                 }
             }
         }
-        // ---- write h_V (and the decoder's frozen encoder state), stage the projection operands ----
+        // ---- stage the projection operands, then write h_V (and the decoder's frozen encoder state): the global stores come after the
+        //      hand-off so that the projection GEMMs do not wait for them (the hand-off's fence drains the thread's memory operations) ----
+        auto write_state = [&]() {
 #pragma unroll
-        for (int i = 0; i < NPTH; ++i) {
-            if (live(i)) {
-                p.hV[gnode(i) * 128 + fl] = v[i];
-                if (p.write_enc) p.hVenc[gnode(i) * 128 + fl] = v[i];
+            for (int i = 0; i < NPTH; ++i) {
+                if (live(i)) {
+                    p.hV[gnode(i) * 128 + fl] = v[i];
+                    if (p.write_enc) p.hVenc[gnode(i) * 128 + fl] = v[i];
+                }
             }
-        }
+        };
+        if (p.n_proj == 0) write_state();
         if (p.n_proj > 0) {
             store_act(act_tile(0), v);
             if (enc_mode) {
@@ -392,6 +396,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                 store_act(act_tile(1), hp);
             }
             publish();
+            write_state();
             // ---- EP: own halves (+ bias) and gathered halves (+ residue-type table) -> P16 (fp16) ----
             wait_mma();
             for (int j = 0; j < p.n_proj; ++j) {
