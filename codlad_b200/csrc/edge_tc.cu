@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 }
                 __syncwarp();
             };
+            cmark(6, 0);
             mbar_wait(smem_u32(&sBar[0]), 0);                         // weights resident
+            cmark(7, 0);
             uint32_t round = 0;
             if (MODE == EDGE_ENC_EDGE) {
                 for (int t0 = tile_begin; t0 < tile_end; t0 += tile_stride, ++round) {

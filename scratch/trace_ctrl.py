@@ -23,7 +23,7 @@ pl.run_edge_kernel(mode, 1); torch.cuda.synchronize()
 tr = pl.buffer("tc_trace").cpu().tolist()
 ev = []
 names = {"epi": ["E1 begin", "E1 acc ready", "E1 math done", "E1 handed off", "E2 begin", "E2 acc ready", "E2 math done", "E2 handed off", "drain begin", "drain acc ready", "drain done"],
-         "mma": ["saw E1 done", "MMA2 issued", "saw E2 done", "saw drained", "saw load landed", "MMA1 issued"],
+         "mma": ["saw E1 done", "MMA2 issued", "saw E2 done", "saw drained", "saw load landed", "MMA1 issued", "warp start", "weights resident"],
          "tma": ["saw slot free", "load issued"]}
 for who, base in (("epi", 0), ("mma", 5120), ("tma", 5632)):
     n = tr[base]
