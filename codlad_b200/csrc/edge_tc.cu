@@ -5,24 +5,31 @@
 //
 //   * edge state h_E, activations and weights are fp16 (kind::f16 MMA, fp32 accumulation in TMEM).  fp16 rather
 //     than bf16: same tensor rate, 8x finer mantissa, and every operand here is LayerNorm/GELU-bounded.
-//   * one persistent CTA per SM: 16 epilogue warps + one MMA-issuing lane + one TMA-issuing lane.  The layer weights
-//     stay resident in shared memory (SWIZZLE_128B, K-major, loaded once by TMA); FOUR tiles are in flight (four
-//     32 KB operand buffers, four 128-column TMEM accumulators).  The epilogue warps run the stages round-robin
-//     E1(0..3) E2(0..3) E3(0..3), so between two stages of a tile the other three tiles' stages run and cover its
-//     MMA / TMA latency; the control lanes issue every MMA and TMA the moment its inputs are ready.
-//     A tile = NPT whole nodes (NPT*K <= 128 neighbour rows) of one ensemble member: the neighbour sum is tile-local.
+//   * one persistent CTA per SM over a contiguous, balanced range of tiles: 16 epilogue warps + an MMA warp + a TMA warp (both
+//     control warps run warp-wide and issue through elect.sync).  The layer weights stay resident in shared memory
+//     (SWIZZLE_128B, K-major, loaded once by TMA); FOUR tiles are in flight (four 32 KB operand buffers, four 128-column TMEM
+//     accumulators).  The epilogue warps run the stages round-robin E1(0..3) E2(0..3) E3(0..3), so between two stages of a
+//     tile the other three tiles' stages run and cover its MMA / TMA latency; the control warps issue every MMA and TMA the
+//     moment its inputs are ready.  A tile = NPT whole nodes (NPT*K <= 128 neighbour rows) of one ensemble member: the
+//     neighbour sum is tile-local.
 //   * epilogue thread (row r, column quarter cq): the four warps that can address a TMEM lane quarter split the 128
-//     accumulator columns of every row, so all 16 warps work on ONE tile stage at a time (the stages are MUFU-bound).
+//     accumulator columns of every row, so all 16 warps work on ONE tile stage at a time.
 //   * per tile: TMA loads the h_E rows (contiguous in HBM) into a swizzled K-major A tile -> MMA 1 (W?b h_E) ->
-//     E1: accumulator from TMEM, + own half Pa[i] (L1 broadcast) + gathered half Pc[j] (fp16, 256-bit loads from L2),
-//     GELU, fp16 activation back into the same smem tile -> MMA 2 -> E2 (+b, GELU) ->
+//     E1: accumulator from TMEM, + own half Pa[i] (L1 broadcast) + gathered half Pc[j] (fp16, 256-bit loads from L2, issued
+//     inside the stage: holding a prefetch in registers costs more than its latency), 2 GELU, fp16 activation back into the
+//     same smem tile -> MMA 2 -> E2 (+b, 2 GELU) ->
 //        ENC_NODE / DEC : the masked neighbour sum is one more (tiny) MMA: S^T[c, q] = sum_r G[r, c] * Ind[q, r]
-//                         with the activation tile reused as an MN-major A operand and a 16-row indicator B; E3 stores S;
-//        ENC_EDGE       : MMA 3 (W13) -> E3: +residual, LayerNorm (row statistics exchanged between the two column
-//                         halves through 1 KB of smem), adaLN modulate/gate -> fp16 tile -> TMA store.
+//                         with the activation tile reused as an MN-major A operand and a 16-row indicator B (holding the
+//                         1/2 of the 2 GELU); slot s is drained (sums read out of TMEM, S stored) by column group s, one
+//                         stage later;
+//        ENC_EDGE       : MMA 3 (W13) -> the TMA warp re-loads the tile's original rows (residual) -> E3: +residual,
+//                         LayerNorm (row statistics exchanged between the four column quarters through drained TMEM
+//                         columns), adaLN modulate/gate -> fp16 tile -> TMA store.
 //   * epilogue arithmetic is packed fp16 (HFMA2); GELU uses tanh.approx (one MUFU per element) on a refitted 2-term
 //     inner polynomial: |err| < 2.8e-4 abs against erf-GELU before the MUFU's own 2^-11 relative error -- the same
 //     order as the fp16 rounding of the activation it feeds.  (The fp32 tier uses erff.)
+//   * the stage bodies sit at the 96-register cap of an 18-warp CTA: what is kept live across a stage (prefetch buffers, debug
+//     timelines, duplicated stage bodies) costs more than it saves -- see DESIGN.md section 4.
 #include <cstring>
 #include "model.h"
 #include "tc_common.cuh"
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             mbar_init(smem_u32(&sBar[13 + g]), 1);
             mbar_init(smem_u32(&sBar[17 + g]), 1);
             mbar_init(smem_u32(&sBar[21 + g]), 1);
-            mbar_init(smem_u32(&sBar[25 + g]), 4);                     // ENC_NODE / DEC: accumulator drained (the 4 warps of column quarter 0)
+            mbar_init(smem_u32(&sBar[25 + g]), 4);                     // ENC_NODE / DEC: accumulator drained (the 4 warps of column group g)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
