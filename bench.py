@@ -187,6 +187,44 @@ def run_reference(args):
     }))
 
 
+# ------------------------------------------------------------------------------------------------ evaluation-step kernel
+def run_metrics(args):
+    """`--workload metrics`: the evaluation-step kernel (cb2_eval_bond_graphs) on the ensemble configs[1]
+    produces, with the CPU oracle port of the reference's eval_sample_qualities timed beside it.  Not the bench line."""
+    from codlad_b200 import metrics, sampler, synthetic, weights
+    torch.set_grad_enabled(False)
+    prot = synthetic.make_protein(L_RES, 1, seed=1002)
+    fs = sampler.frames_from_batch(synthetic.collate(prot), prot.info, ENSEMBLE)
+    bm = sampler.Backmapper(weights.init_denoiser_state(0), weights.init_vae_decode_state(0), "N6", num_sampling_steps=10, precision=args.precision)
+    xyz = bm.sample(bm.upload(fs), fs, generator=torch.Generator(device="cuda").manual_seed(1))["xyz"]
+    na = int(fs.num_atoms[0])
+    num = [na] * ENSEMBLE
+    ref = xyz[:na].repeat(ENSEMBLE, 1).contiguous()              # every member against member 0
+    z = torch.tensor([7, 6, 6, 8, 6, 6, 16, 8, 1], dtype=torch.int64).repeat(xyz.shape[0] // 9 + 1)[:xyz.shape[0]].cuda()
+    for _ in range(max(args.warmup, 3)):
+        metrics.bond_graph_stats(ref, xyz, z, num)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(args.steps, 20)
+    a.record()
+    for _ in range(reps):
+        counts, _ = metrics.bond_graph_stats(ref, xyz, z, num)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    from oracle import restate as R                               # CPU baseline leg
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    c_ref, _ = R.sample_quality_stats(ref.cpu(), xyz.cpu(), z.cpu(), num)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"metric": "bond-graph comparisons (structures scored per second)", "value": ENSEMBLE / (ms * 1e-3), "unit": "structures/s",
+                      "structures": ENSEMBLE, "atoms_per_structure": na, "gpu_ms_per_call": ms, "atom_pairs_per_s": 2 * ENSEMBLE * na * na / (ms * 1e-3),
+                      "cpu_baseline": {"value": ENSEMBLE / cpu_s, "unit": "structures/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "the same 10 structures, oracle.restate.sample_quality_stats"},
+                      "counts_equal_oracle": bool(torch.equal(counts.cpu(), c_ref)),
+                      "note": "gpu_ms_per_call is the public call (input checks, one small H2D copy of the offsets, two kernels)"}))
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -196,10 +234,15 @@ def main():
     ap.add_argument("--impl", default="codlad_b200", choices=["codlad_b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CB2_PRECISION", "f16"), choices=["f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the bench line; c3 / c4 = scale checks")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["metrics"],
+                    help="c2 = the bench line; c3 / c4 = scale checks; metrics = the evaluation-step kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "metrics":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: codlad_b200 has no CPU fallback")
+        return run_metrics(args)
     args.warmup = max(args.warmup, 3)
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
