@@ -580,7 +580,7 @@ static int enqueue_loop(cb2_plan* h, float* x, const float* noise, cudaStream_t 
     for (int step = p.coef_steps - 1; step >= 0; --step) {
         const float* mod_row = p.mod + (size_t)step * CB2_MOD_TOTAL;     // every member shares the step -> stride 0
         if (int e = run_forward(p, cur, mod_row, 0, noise + (size_t)step * n3, nxt, p.coef + (size_t)step * 8, s)) {
-            char prev[900];
+            char prev[1024];
             snprintf(prev, sizeof(prev), "%s", g_err);
             const unsigned int* tl = edge_tc_trap_log();
             if (tl != nullptr) {
