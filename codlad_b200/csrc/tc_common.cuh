@@ -210,6 +210,9 @@ __device__ __forceinline__ __half2 gelu2_h2(__half2 x) {
     const __half2 x2 = __hmul2(x, x);
     const __half2 pl = __hfma2(x2, __float2half2_rn(0.03470094f), __float2half2_rn(0.80015698f));
     const __half2 u = __hmul2(x, pl);
+#ifdef CB2_X_NOTANH      // timing ablation: everything but the two MUFU.TANH + PRMT of the pair
+    return __hfma2(x, u, x);
+#endif
     uint32_t t;
     asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(as_u32(u)));
     return __hfma2(x, as_h2(t), x);
