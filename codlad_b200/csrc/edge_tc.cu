@@ -604,6 +604,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         // row statistics: the four column quarters of a row exchange their partial sums through accumulator
                         // columns this thread has already drained (its own first two) -- tcgen05.st, one barrier, tcgen05.ld;
                         // summed in a fixed order, so the result is deterministic
+#ifdef CB2_X_NOXCHG                                                     // timing ablation: no exchange of the row statistics
+                        const float tsum = 4.0f * sum, tsq = 4.0f * sq;
+#else
                         tmem_st2(tmem_lane + (uint32_t)(s * 128), sum, sq);
                         tc_fence_before();
                         row_quarter_sync(quarter);
@@ -611,6 +614,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         float part[8];
                         tmem_ld2_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128), 32u, part);
                         const float tsum = (part[0] + part[2]) + (part[4] + part[6]), tsq = (part[1] + part[3]) + (part[5] + part[7]);
+#endif
                         const float mean = tsum * (1.0f / 128.0f);
                         const float rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
                         const __half2 rstd2 = __float2half2_rn(rstd), nmr2 = __float2half2_rn(-mean * rstd);
