@@ -604,7 +604,8 @@ int cb2_plan_sample(cb2_plan* h, float* x, const float* noise, int use_graph, vo
     if (!h->frames_ready || p.coef_steps <= 0) { set_error("sample: set_frames / set_schedule must be called first"); return 1; }
     cudaStream_t s = (cudaStream_t)stream;
     if (!use_graph) return enqueue_loop(h, x, noise, s);
-    if (!p.graph || p.graph_key[0] != x || p.graph_key[1] != noise || p.graph_steps != p.coef_steps) {
+    // (kernel variants are chosen at capture time from the geometry: a frame set with / without padded residues needs its own graph)
+    if (!p.graph || p.graph_key[0] != x || p.graph_key[1] != noise || p.graph_steps != p.coef_steps || p.graph_all_full != p.all_full) {
         if (p.graph) { cudaGraphExecDestroy(p.graph); p.graph = nullptr; }
         cudaStream_t cs;
         CB2_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -624,7 +625,7 @@ int cb2_plan_sample(cb2_plan* h, float* x, const float* noise, int use_graph, vo
         cudaGraphDestroy(g);
         cudaStreamDestroy(cs);
         if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); p.graph = nullptr; return (int)ce; }
-        p.graph_key[0] = x; p.graph_key[1] = noise; p.graph_steps = p.coef_steps;
+        p.graph_key[0] = x; p.graph_key[1] = noise; p.graph_steps = p.coef_steps; p.graph_all_full = p.all_full;
     }
     CB2_CUDA(cudaGraphLaunch(p.graph, s));
     p.launches += 16LL * p.coef_steps;

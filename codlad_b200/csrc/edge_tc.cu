@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         // (MMA and TMA issue are split because a thread's tcgen05.mma stalls behind its own in-flight bulk copies.)
         // Both warps run their control flow with all 32 lanes and issue through elect.sync (see elect_one()).
         auto T_u32 = [&](int g) { return smem_u32(sT + g * TILE_BYTES); };
-#ifdef CB2_TRACE_CTRL                                                   // debug builds (scratch/build_variant.sh -DCB2_TRACE_CTRL): timeline of CTA 0's
+#ifdef CB2_TRACE_CTRL                                                   // debug builds (tools/dev/build_variant.sh -DCB2_TRACE_CTRL): timeline of CTA 0's
         // control warps (lane 0): MMA warp -> trace[5120..], TMA warp -> trace[5632..]
         unsigned long long* ctr = (p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0) ? p.trace + (tid >= EPI_THREADS + 32 ? 5632 : 5120) : nullptr;
         int n_ctr = 0;
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                 tc_fence_after();
                 mark(1, s);
                 float acc0[16], acc1[16];
-#ifdef CB2_X_NOLDTM                                                     // timing ablations (scratch/build_variant.sh), never in the product build
+#ifdef CB2_X_NOLDTM                                                     // timing ablations (tools/dev/build_variant.sh), never in the product build
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));

@@ -89,6 +89,7 @@ struct Plan {
     cudaGraphExec_t graph = nullptr;
     const void* graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
     int graph_steps = 0;
+    bool graph_all_full = false;    // the captured launches chose the masked / unmasked message kernels from all_full
     std::vector<void*> allocs;
     void* tmaps = nullptr;          // host-side CUtensorMap storage of the tcgen05 edge kernels
     void* node_tc = nullptr;        // ... and of the tcgen05 node kernels

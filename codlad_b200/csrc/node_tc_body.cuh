@@ -145,7 +145,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
         } else if (warp == 16) {
             // ------------------------------------------------------------------ MMA lane: D[feature, node] = W[feature, :] . act[node, :]
             // (the whole warp runs the control flow; the instructions are issued by an elected lane)
-#ifdef CB2_TRACE_CTRL                                                   // debug builds only (scratch/build_variant.sh -DCB2_TRACE_CTRL)
+#ifdef CB2_TRACE_CTRL                                                   // debug builds only (tools/dev/build_variant.sh -DCB2_TRACE_CTRL)
             unsigned long long* ctrace = (p.trace != nullptr && blockIdx.x == 0 && lane == 0) ? p.trace + 512 : nullptr;
             int n_ct = 0;
             auto cmark = [&](int ev) {

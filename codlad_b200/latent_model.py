@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from . import weights
+from . import batching, weights
 from .engine import DenoiserEngine, Plan
 
 
@@ -51,6 +51,7 @@ class ProteinMPNN_diffusion_new(nn.Module):
             _register(self, name, t)
         self._engine = None
         self._plans = {}
+        self._last = None
         self.eval()
 
     # -- packed device copy of the weights (rebuilt after load_state_dict) ---------------------------
@@ -62,9 +63,10 @@ class ProteinMPNN_diffusion_new(nn.Module):
 
     def refresh(self):
         """Drop the packed weights and every cached plan (call after mutating parameters in place)."""
-        for p in self._plans.values():
-            p.close()
+        for ent in self._plans.values():
+            ent["plan"].close()
         self._plans.clear()
+        self._last = None
         if self._engine is not None:
             self._engine.close()
         self._engine = None
@@ -82,31 +84,44 @@ class ProteinMPNN_diffusion_new(nn.Module):
     # -- geometry ------------------------------------------------------------------------------------
     def plan_for(self, batch: dict, n_members: int) -> Plan:
         """Plan for the frames of `batch` with `n_members` batch rows (n_members == F, or 2F for test.py's doubled
-        batch, latent_model.py:178-186 / test.py:505-521).  Cached on the identity of batch['CG_nxyz']."""
-        cg = batch["CG_nxyz"]
-        num = batch["num_CGs"]
-        key = (cg.data_ptr(), tuple(cg.shape), int(n_members), cg._version)
-        plan = self._plans.get(key)
-        if plan is not None:
-            return plan
-        num_l = [int(v) for v in num.tolist()]
+        batch, latent_model.py:178-186 / test.py:505-521).
+
+        Plans are cached per GEOMETRY (F, n_members, Lmax) and remember the CONTENT they were built for: a new batch of
+        the same shape (the next frames of the reference driver loop, test.py:481-534) re-runs the per-frame precompute
+        on the existing plan instead of allocating a new one, and a batch is only taken as "the same" if it is the very
+        tensor object the plan was built from (a held reference, so its storage cannot be recycled) at the same version,
+        or if its bytes compare equal -- never by address alone."""
+        cg, num = batch["CG_nxyz"], batch["num_CGs"]
+        ent = self._last
+        if (ent is not None and ent["cg_ref"] is cg and ent["num_ref"] is num and ent["version"] == (cg._version, num._version)
+                and ent["n_members"] == int(n_members)):
+            return ent["plan"]
+        num_l = tuple(int(v) for v in num.tolist())
         F, L = len(num_l), max(num_l)
         if n_members % F != 0:
             raise ValueError(f"batch of {n_members} rows over {F} frames")
-        cgc = cg.detach().to("cpu", torch.float32)
-        X = torch.zeros(F, L, 3)
-        z = torch.zeros(F, L, dtype=torch.int32)
-        o = 0
-        for f, n in enumerate(num_l):
-            X[f, :n] = cgc[o:o + n, 1:]
-            z[f, :n] = cgc[o:o + n, 0].to(torch.int32)
-            o += n
-        plan = Plan(self.engine(), F, n_members, L, self.precision)
-        plan.set_frames(X, torch.tensor(num_l, dtype=torch.int32), z, torch.arange(F, dtype=torch.int32).repeat(n_members // F))
-        if len(self._plans) >= 4:                      # a sampling run alternates between very few geometries
-            self._plans.pop(next(iter(self._plans))).close()
-        self._plans[key] = plan
-        return plan
+        geo = (F, int(n_members), L)
+        cg_host = cg.detach().to("cpu", torch.float32)
+        ent = self._plans.get(geo)
+        if ent is None:
+            if len(self._plans) >= 4:                  # a sampling run alternates between very few geometries
+                self._plans.pop(next(iter(self._plans)))["plan"].close()
+            ent = {"plan": Plan(self.engine(), F, int(n_members), L, self.precision), "cg": None, "num": None, "n_members": int(n_members),
+                   "bufs": None, "schedule": None}
+            self._plans[geo] = ent
+        if ent["num"] != num_l or ent["cg"] is None or not torch.equal(ent["cg"], cg_host):
+            X, z = batching.pad_frames(cg_host, torch.tensor(num_l), L)
+            ent["plan"].set_frames(X, torch.tensor(num_l, dtype=torch.int32), z, torch.arange(F, dtype=torch.int32).repeat(n_members // F))
+            ent["cg"], ent["num"] = cg_host.clone(), num_l
+        ent["cg_ref"], ent["num_ref"], ent["version"] = cg, num, (cg._version, num._version)
+        self._last = ent
+        return ent["plan"]
+
+    def _entry_of(self, plan: Plan) -> dict:
+        for ent in self._plans.values():
+            if ent["plan"] is plan:
+                return ent
+        raise KeyError("plan is not cached by this module")
 
     def forward(self, x, t, y=None, mask=None, batch=None, x_self_cond=None):
         """x [B, L, 3], t [B] (original 0..999 scale; int or float), mask [B, L] bool, batch = reference batch dict.
@@ -128,21 +143,29 @@ class _FusedSampler:
 
     def sample_loop(self, diffusion, shape, noise, model_kwargs, device, step_noise):
         batch = model_kwargs.get("batch")
-        plan = self.model.plan_for(batch, shape[0])
-        plan.set_schedule(diffusion.timestep_map, diffusion.coef_table())
+        model = self.model
+        plan = model.plan_for(batch, shape[0])
+        ent = model._entry_of(plan)
+        T = diffusion.num_timesteps
+        sched_key = (T, tuple(int(v) for v in diffusion.timestep_map))
+        if ent["schedule"] != sched_key:                 # (re-)tabulate the adaLN rows only when the schedule changes: it drops the graph
+            plan.set_schedule(diffusion.timestep_map, diffusion.coef_table())
+            ent["schedule"] = sched_key
         dev = plan.device
-        x = torch.empty(*shape, device=dev, dtype=torch.float32)
+        bufs = ent["bufs"]
+        if bufs is None or bufs[1].shape[0] != T:         # persistent x / noise buffers: the CUDA graph of the loop is keyed on them
+            bufs = ent["bufs"] = (torch.empty(*shape, device=dev, dtype=torch.float32), torch.empty(T, *shape, device=dev, dtype=torch.float32))
+        x, eps = bufs
         if noise is not None:
-            x.copy_(noise)
+            x.copy_(noise, non_blocking=True)
         else:
             torch.randn(*shape, device=dev, out=x)
-        T = diffusion.num_timesteps
         if step_noise is not None:
-            eps = step_noise.to(dev, torch.float32).contiguous()
+            eps.copy_(step_noise, non_blocking=True)
         else:
-            eps = torch.randn(T, *shape, device=dev)
-        plan.sample(x, eps, use_graph=False)       # x / eps are fresh tensors: a cached graph would be keyed on stale pointers
-        return x
+            torch.randn(T, *shape, device=dev, out=eps)
+        plan.sample(x, eps, use_graph=True)
+        return x.clone()                                 # the caller owns its result; the buffer is reused by the next call
 
 
 def fused_sampler_for(model):

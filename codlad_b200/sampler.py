@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import topology, weights
+from . import batching, topology, weights
 from .diffusion import create_diffusion
 from .engine import DenoiserEngine, Plan, VaeEngine
 
@@ -65,24 +65,6 @@ class FrameSet:
     def NB(self): return self.frame_of.numel()
 
 
-def directed_csr(nbr: torch.Tensor, n_rows: int):
-    """Undirected or directed [E,2] list -> CSR over `n_rows` rows with columns sorted ascending
-    (make_directed, reference models/gcn_nn.py:54-64).  Returns (row_ptr [n_rows+1], col [E'])."""
-    nbr = nbr.to(torch.int64)
-    if nbr.numel() == 0:
-        return torch.zeros(n_rows + 1, dtype=torch.int32), torch.zeros(0, dtype=torch.int32)
-    a, b = nbr[:, 0], nbr[:, 1]
-    if not (bool((a > b).any()) and bool((b > a).any())):
-        nbr = torch.cat([nbr, nbr.flip(1)], dim=0)
-    key = nbr[:, 0] * (int(nbr.max()) + 1) + nbr[:, 1]
-    order = torch.argsort(key, stable=True)
-    nbr = nbr[order]
-    counts = torch.bincount(nbr[:, 0], minlength=n_rows)
-    row_ptr = torch.zeros(n_rows + 1, dtype=torch.int64)
-    row_ptr[1:] = torch.cumsum(counts, 0)
-    return row_ptr.to(torch.int32), nbr[:, 1].to(torch.int32)
-
-
 def frames_from_batch(batch: dict, infos, num_ensemble: int = 1) -> FrameSet:
     """Convert a reference-schema batch dict (CG_collate, utils/dataset_module.py:259-295) of F frames
     plus their `info` tuples (one per frame, or one shared) into a FrameSet with `num_ensemble`
@@ -91,38 +73,29 @@ def frames_from_batch(batch: dict, infos, num_ensemble: int = 1) -> FrameSet:
     F, L = num.numel(), int(num.max())
     cg = batch["CG_nxyz"].cpu().to(torch.float32)
     og = batch["OG_CG_nxyz"].cpu().to(torch.float32)
-    nbr = batch["CG_nbr_list"].cpu().to(torch.int64)
-    if isinstance(infos, tuple) and len(infos) == 3 and torch.is_tensor(infos[0]):
-        infos = [infos] * F
-    X = torch.zeros(F, L, 3)
-    ca_full = torch.zeros(F, L + 2, 3)
-    cg_z = torch.zeros(F, L, dtype=torch.int32)
+    shared = isinstance(infos, tuple) and len(infos) == 3 and torch.is_tensor(infos[0])
+    X, cg_z = batching.pad_frames(cg, num, L)
+    ca_full = batching.pad_frames(og, num + 2, L + 2)[0]
     orders = torch.zeros(F, L, 10, 3, dtype=torch.int8)
     orders[..., 1], orders[..., 2] = 1, 2
     slot_atom = torch.full((F, L * 14), -1, dtype=torch.int32)
     num_atoms = torch.zeros(F, dtype=torch.int64)
-    rows, cols = [torch.zeros(1, dtype=torch.int32)], []
-    off = torch.cumsum(num, 0) - num
-    edge_frame = torch.bucketize(nbr[:, 0].contiguous(), torch.cumsum(num, 0), right=True) if nbr.numel() else None
-    e_base = 0
-    for f in range(F):
-        n, o = int(num[f]), int(off[f])
-        X[f, :n] = cg[o:o + n, 1:]
-        cg_z[f, :n] = cg[o:o + n, 0].to(torch.int32)
-        ca_full[f, :n + 2] = og[o + 2 * f:o + 2 * f + n + 2, 1:]
-        permute, atom_idx, atom_orders = infos[f]
-        orders[f, :n] = atom_orders.permute(1, 0, 2).to(torch.int8)
-        slot_atom[f, :n * 14] = topology.slot_to_atom_map(infos[f], n)
-        num_atoms[f] = permute.numel()
-        local = nbr[edge_frame == f] - o if nbr.numel() else nbr
-        rp, col = directed_csr(local, L)
-        rows.append(rp[1:] + e_base)
-        cols.append(col)
-        e_base += int(col.numel())
+    if shared and bool((num == num[0]).all()):
+        n = int(num[0])
+        orders[:, :n] = infos[2].permute(1, 0, 2).to(torch.int8)[None]
+        slot_atom[:, :n * 14] = topology.slot_to_atom_map(infos, n)[None]
+        num_atoms[:] = infos[0].numel()
+    else:
+        per_frame = [infos] * F if shared else infos
+        for f in range(F):
+            n = int(num[f])
+            permute, _, atom_orders = per_frame[f]
+            orders[f, :n] = atom_orders.permute(1, 0, 2).to(torch.int8)
+            slot_atom[f, :n * 14] = topology.slot_to_atom_map(per_frame[f], n)
+            num_atoms[f] = permute.numel()
+    csr_row, csr_col = batching.batch_csr(batch["CG_nbr_list"], num, L)
     frame_of = torch.arange(F, dtype=torch.int32).repeat(num_ensemble)
-    return FrameSet(X, ca_full, cg_z, num.to(torch.int32), torch.cat(rows).to(torch.int32),
-                    torch.cat(cols).to(torch.int32) if cols else torch.zeros(0, dtype=torch.int32),
-                    orders, slot_atom, num_atoms, frame_of)
+    return FrameSet(X, ca_full, cg_z, num.to(torch.int32), csr_row, csr_col, orders, slot_atom, num_atoms, frame_of)
 
 
 class Backmapper:

@@ -13,17 +13,30 @@ import torch
 from torch import nn
 
 from . import _native as N
-from . import weights
+from . import batching, weights
 from .engine import Plan, VaeEngine
 from .latent_model import _register
-from .sampler import VAE_DATA, directed_csr
+from .sampler import VAE_DATA
 
 
-def get_norm_feature(feature, feature_type="latent", norm_channel=True, norm_single=False, norm_in=True, dataname="PED_N6"):
-    """utils/dataset_module.py:230-256: latent (de)normalisation with the shipped mean / std 3-vectors
-    (datasets/miu_and_sigma/*.pt).  `dataname` = f"{data}_{vae_type}" as in the reference."""
-    data, vae_type = dataname.split("_")[0], dataname.split("_")[-1]
-    mean, std = (torch.tensor(v, device=feature.device, dtype=feature.dtype) for v in weights.LATENT_STATS[(vae_type, data)])
+def get_norm_feature(feature, feature_type, norm_channel=True, norm_single=False, norm_in=True, dataname="PED"):
+    """utils/dataset_module.py:230-256: latent (de)normalisation with the shipped mean / std vectors
+    (datasets/miu_and_sigma/{dataname}_{feature_type}_x_{mean,std}.pt).  Same argument meaning as the reference:
+    `feature_type` is the VAE type ('N6' / 'K3' / 'K4'), `dataname` the data set ('PED' / 'PDB' / 'Atlas'), as
+    test.py:548 calls it -- get_norm_feature(samples, args.vae_type, norm_channel=..., norm_single=..., norm_in=False,
+    dataname=args.data_type).  'IDRome_test_7' is remapped to the data set the VAE type was trained on (:239-246).
+    The `_single` statistics files (norm_single=True) are not shipped with the reference and are not tabulated here."""
+    if norm_single:
+        raise NotImplementedError("get_norm_feature: the '_single' statistics (norm_single=True) are not shipped with the reference")
+    if dataname == "IDRome_test_7":
+        if feature_type not in VAE_DATA:
+            raise KeyError(f"get_norm_feature: no data set for feature_type {feature_type!r}")
+        dataname = VAE_DATA[feature_type]
+    key = (feature_type, dataname)
+    if key not in weights.LATENT_STATS:
+        raise FileNotFoundError(f"get_norm_feature: no statistics for {dataname}_{feature_type}_x (known: "
+                                f"{sorted(f'{d}_{v}_x' for v, d in weights.LATENT_STATS)})")
+    mean, std = (torch.tensor(v, device=feature.device, dtype=feature.dtype) for v in weights.LATENT_STATS[key])
     return (feature - mean) / std if norm_in else feature * std + mean
 
 
@@ -63,21 +76,31 @@ class VAE(nn.Module):
         for name, t in weights.init_vae_decode_state(init_seed, self.angle_variant, stats).items():
             _register(self, name, t)
         self._engine = None
+        self._decode_plans = {}
         self.eval()
 
-    def load_state_dict(self, state_dict, strict: bool = False, **kw):
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Strict for the decode-side key set like the reference's load after remove_key (utils/model_module.py:118-120):
+        a checkpoint that lacks any tensor `latent_decode` reads fails loudly instead of decoding with random weights.
+        Encoder / prior tensors of a full checkpoint are ignored (that half is not built here); a DDP 'module.' prefix is
+        stripped like the denoiser loader does."""
+        state_dict = {k.removeprefix("module."): v for k, v in state_dict.items()}
         own = self.state_dict()
-        picked = {k: v for k, v in state_dict.items() if k in own}        # encoder / prior tensors of a full checkpoint are ignored
+        picked = {k: v for k, v in state_dict.items() if k in own}
         if "quantize._codebook.embed" in picked:
             picked["quantize._codebook.embed"] = picked["quantize._codebook.embed"].reshape(own["quantize._codebook.embed"].shape)
         missing = [k for k in own if k not in picked]
         if strict and missing:
-            raise KeyError(f"missing decode-side tensors: {missing[:5]}...")
+            raise RuntimeError(f"VAE.load_state_dict: {len(missing)} decode-side tensor(s) missing from the checkpoint: {missing[:5]}"
+                               f"{'...' if len(missing) > 5 else ''}")
         out = super().load_state_dict(picked, strict=False, **kw)
         self.refresh()
         return out
 
     def refresh(self):
+        for plan in self._decode_plans.values():
+            plan.close()
+        self._decode_plans.clear()
         if self._engine is not None:
             self._engine.close()
         self._engine = None
@@ -91,32 +114,24 @@ class VAE(nn.Module):
     # -- reference surface ---------------------------------------------------------------------------
     def latent_decode(self, latent, mask, batch):
         """vae_model.py:830-839: quantise -> map_out -> IC decoder.  latent [B, L, 3] (already de-normalised),
-        mask [B, L] bool, batch = reference batch dict (CG_nxyz, num_CGs, CG_nbr_list).  -> (None, ic_recon [sum L, 13, 3])."""
-        num = [int(v) for v in batch["num_CGs"].tolist()]
+        mask [B, L] bool, batch = reference batch dict (CG_nxyz, num_CGs, CG_nbr_list).  -> (None, ic_recon [sum L, 13, 3]).
+        The decode-only plan (buffers) is kept per geometry (B, L); the frame data are re-uploaded on every call."""
+        num = batch["num_CGs"].to(torch.int64).cpu()
         B, L = latent.shape[0], latent.shape[1]
-        if len(num) != B or max(num) != L:
+        if num.numel() != B or int(num.max()) != L:
             raise ValueError("latent_decode: latent must be padded to the batch's max length, one row per frame")
-        cg = batch["CG_nxyz"].detach().to("cpu", torch.float32)
-        nbr = batch["CG_nbr_list"].detach().to("cpu", torch.int64)
-        X = torch.zeros(B, L, 3)
-        z = torch.zeros(B, L, dtype=torch.int32)
-        rows, cols, e_base, o = [torch.zeros(1, dtype=torch.int32)], [], 0, 0
-        ends = torch.cumsum(torch.tensor(num), 0)
-        frame = torch.bucketize(nbr[:, 0].contiguous(), ends, right=True) if nbr.numel() else None
-        for f, n in enumerate(num):
-            X[f, :n] = cg[o:o + n, 1:]
-            z[f, :n] = cg[o:o + n, 0].to(torch.int32)
-            rp, col = directed_csr(nbr[frame == f] - o if nbr.numel() else nbr, L)
-            rows.append(rp[1:] + e_base)
-            cols.append(col)
-            e_base += int(col.numel())
-            o += n
-        plan = Plan(None, B, B, L, "fp32")
-        plan.set_frames(X, torch.tensor(num, dtype=torch.int32), z, torch.arange(B, dtype=torch.int32))
-        orders = torch.zeros(B, L, 10, 3, dtype=torch.int8)
-        plan.set_topology(self.engine(), torch.zeros(B, L + 2, 3), torch.cat(rows).to(torch.int32),
-                          torch.cat(cols).to(torch.int32) if cols else torch.zeros(0, dtype=torch.int32), orders,
-                          torch.full((B, L * 14), -1, dtype=torch.int32), torch.zeros(B, dtype=torch.int64))
+        X, z = batching.pad_frames(batch["CG_nxyz"], num, L)
+        csr_row, csr_col = batching.batch_csr(batch["CG_nbr_list"], num, L)
+        plan = self._decode_plans.get((B, L))
+        if plan is None:
+            if len(self._decode_plans) >= 4:
+                self._decode_plans.pop(next(iter(self._decode_plans))).close()
+            plan = self._decode_plans[(B, L)] = Plan(None, B, B, L, "fp32")
+            plan._static = (torch.zeros(B, L + 2, 3), torch.zeros(B, L, 10, 3, dtype=torch.int8),
+                            torch.full((B, L * 14), -1, dtype=torch.int32), torch.zeros(B, dtype=torch.int64))      # unused by the IC decoder
+        plan.set_frames(X, num.to(torch.int32), z, torch.arange(B, dtype=torch.int32))
+        ca, orders, slots, offs = plan._static
+        plan.set_topology(self.engine(), ca, csr_row, csr_col, orders, slots, offs)
         _, _, ic, _ = plan.decode(self.engine(), latent, denorm=False, num_atoms_total=None, want_ic=True)
         m = mask.to(ic.device) if mask is not None else torch.ones(B, L, dtype=torch.bool, device=ic.device)
         return None, ic[m]                                         # restore_shape: ragged [sum L, 13, 3]

@@ -42,7 +42,7 @@ def ref_denoiser(k_neighbors=64, seed=0):
     return m, sd
 
 
-def golden_denoiser(name, L, frames, k_neighbors, prot_seed, x_seed, t_list, lengths=None):
+def golden_denoiser(name, L, frames, k_neighbors, prot_seed, x_seed, t_list, lengths=None, slim=False):
     """One denoiser forward.  `lengths` (ragged case) builds a batch of proteins of different
     length, padded by the reference's own reshape_and_create_mask."""
     m, _ = ref_denoiser(k_neighbors)
@@ -70,6 +70,11 @@ def golden_denoiser(name, L, frames, k_neighbors, prot_seed, x_seed, t_list, len
         E, E_idx = m.features(X, mask.int(), torch.arange(Lmax)[None].expand(B, -1), torch.ones(B, Lmax))
         D_nb, _, _ = m.features._dist(X, mask.int())
         out = m(x, t, None, mask=mask, batch=batch)
+    if slim:      # large shapes: every 8th distance row, no feature sample (the small cases pin those stages)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), E_idx=E_idx.numpy().astype(np.int16), D_nb=D_nb.numpy()[:, ::8], out=out.numpy(),
+                            meta=np.array([L, frames, k_neighbors, prot_seed, x_seed] + list(t_list)))
+        print(name, "out", tuple(out.shape), float(out.abs().max()))
+        return
     np.savez_compressed(os.path.join(OUT, name + ".npz"), E_idx=E_idx.numpy().astype(np.int16), D_nb=D_nb.numpy(),
                         E_sample=E[:, ::7, ::5].numpy(), out=out.numpy(),
                         meta=np.array([L, frames, k_neighbors, prot_seed, x_seed] + list(t_list)))
@@ -103,6 +108,51 @@ def golden_sampler(name, L, prot_seed, z_seed, noise_seed, steps=100):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), timestep_map=np.array(diffusion.timestep_map),
                         meta=np.array([L, prot_seed, z_seed, noise_seed, steps]), **keep)
     print(name, {k: float(np.abs(v).max()) for k, v in keep.items()})
+
+
+def golden_denoiser_members(name, L, members, k_neighbors, prot_seed, x_seed, t_list):
+    """One denoiser forward on ONE frame with `members` batch rows (ensemble members: the reference sees `members` copies of
+    the frame in its batch dict) -- the BASELINE configs[1] / configs[3] geometry.  Only the model output and the
+    neighbour indices of the frame are stored (the distances are pinned bit-exactly against the oracle elsewhere)."""
+    m, _ = ref_denoiser(k_neighbors)
+    prot = synthetic.make_protein(L, 1, seed=prot_seed)
+    batch = synthetic.collate(prot, frames=[0] * members)
+    mask = torch.ones(members, L, dtype=torch.bool)
+    x = synthetic.latent_noise((members, L, 3), x_seed)
+    batch["randn"] = torch.zeros(members, L)
+    t = torch.tensor(t_list, dtype=torch.int64)
+    with torch.no_grad():
+        X = prot.ca_full[:, 1:-1].contiguous()
+        _, E_idx = m.features(X, torch.ones(1, L, dtype=torch.int32), torch.arange(L)[None], torch.ones(1, L))
+        D_nb, _, _ = m.features._dist(X, torch.ones(1, L, dtype=torch.int32))
+        out = m(x, t, None, mask=mask, batch=batch)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), E_idx=E_idx.numpy().astype(np.int16), D_nb=D_nb.numpy().astype(np.float32)[:, ::8],
+                        out=out.numpy(), meta=np.array([L, members, k_neighbors, prot_seed, x_seed] + list(t_list)))
+    print(name, "out", tuple(out.shape), float(out.abs().max()))
+
+
+def golden_sampler_members(name, L, members, prot_seed, z_seed, noise_seed, steps):
+    """`steps`-step p_sample_loop of `members` ensemble members on one frame (configs[1] geometry, short schedule)."""
+    m, _ = ref_denoiser()
+    prot = synthetic.make_protein(L, 1, seed=prot_seed)
+    batch = synthetic.collate(prot, frames=[0] * members)
+    batch["randn"] = torch.zeros(members, L)
+    mask = torch.ones(members, L, dtype=torch.bool)
+    z = synthetic.latent_noise((members, L, 3), z_seed)
+    noises = synthetic.latent_noise((steps, members, L, 3), noise_seed)
+    diffusion = create_diffusion(str(steps))
+    it = iter(list(range(steps))[::-1])
+    real = gd.th.randn_like
+    gd.th.randn_like = lambda x: noises[next(it)].to(x)
+    try:
+        with torch.no_grad():
+            sample = diffusion.p_sample_loop(m.forward, z.shape, z, clip_denoised=False,
+                                             model_kwargs=dict(y=None, mask=mask, batch=batch), device="cpu")
+    finally:
+        gd.th.randn_like = real
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), timestep_map=np.array(diffusion.timestep_map), sample_0=sample.numpy(),
+                        meta=np.array([L, members, prot_seed, z_seed, noise_seed, steps]))
+    print(name, float(sample.abs().max()))
 
 
 def export_c2_decoder():
@@ -245,24 +295,40 @@ def golden_sample_qualities(name, L, frames, seed, sigma):
     print(name, np.array(out).round(4).tolist())
 
 
+GOLDENS = {
+    "denoiser_L64_B1": lambda n: golden_denoiser(n, 64, 1, 64, 1001, 2001, [717]),
+    "denoiser_L70_B2": lambda n: golden_denoiser(n, 70, 2, 64, 1002, 2002, [999, 10]),
+    "denoiser_L100_K48": lambda n: golden_denoiser(n, 100, 1, 48, 1004, 2004, [505]),
+    "denoiser_L40_short": lambda n: golden_denoiser(n, 40, 2, 64, 1006, 2006, [0, 303]),           # K = L < 64
+    "denoiser_ragged": lambda n: golden_denoiser(n, 80, 0, 64, 1005, 2005, [61, 989], lengths=[80, 70]),
+    "sampler_L64_100": lambda n: golden_sampler(n, 64, 1001, 2001, 3001, 100),
+    "decode_L64_N6": lambda n: golden_decode(n, 64, 2, 1001, 4001, False),
+    "decode_L64_K4": lambda n: golden_decode(n, 64, 1, 1001, 4002, True),
+    "decode_L64_N6_c2": lambda n: golden_decode(n, 64, 1, 1001, 4003, False, use_c2=True),
+    "vq_20000": lambda n: golden_vq(n, 20000, 5001),
+    "ic_large_angle_L48": lambda n: golden_ic_large_angle(n, 48, 6001),
+    "training_losses_B6": lambda n: golden_training_losses(n, 6, 24, 7001),
+    "sample_qualities_exact": lambda n: golden_sample_qualities(n, 40, 2, 8001, 0.0),
+    "sample_qualities_noisy": lambda n: golden_sample_qualities(n, 40, 3, 8002, 0.08),
+    # BASELINE.json shapes: configs[1] (300 residues x 10 members), configs[2] (500-residue proteins), configs[3] (2000 residues, k = 48)
+    "denoiser_c2_L300x10": lambda n: golden_denoiser_members(n, 300, 10, 64, 1002, 2102, [999, 989, 747, 500, 500, 252, 131, 10, 0, 0]),
+    "sampler_c2_L300x10_5": lambda n: golden_sampler_members(n, 300, 10, 1002, 2103, 3103, 5),
+    "denoiser_c3_L500_B3": lambda n: golden_denoiser(n, 500, 3, 64, 1013, 2113, [999, 421, 7], slim=True),
+    "denoiser_c4_L2000_K48x2": lambda n: golden_denoiser_members(n, 2000, 2, 48, 1014, 2114, [868, 40]),
+    "decode_c2_L300_N6": lambda n: golden_decode(n, 300, 1, 1002, 4102, False),
+    "decode_c4_L2000_K4": lambda n: golden_decode(n, 2000, 1, 1014, 4114, True),
+}
+
+
 def main():
+    """python -m oracle.make_goldens [name ...]   (no names = every golden)"""
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    export_c2_decoder()
-    golden_denoiser("denoiser_L64_B1", 64, 1, 64, 1001, 2001, [717])
-    golden_denoiser("denoiser_L70_B2", 70, 2, 64, 1002, 2002, [999, 10])
-    golden_denoiser("denoiser_L100_K48", 100, 1, 48, 1004, 2004, [505])
-    golden_denoiser("denoiser_L40_short", 40, 2, 64, 1006, 2006, [0, 303])           # K = L < 64
-    golden_denoiser("denoiser_ragged", 80, 0, 64, 1005, 2005, [61, 989], lengths=[80, 70])
-    golden_sampler("sampler_L64_100", 64, 1001, 2001, 3001, 100)
-    golden_decode("decode_L64_N6", 64, 2, 1001, 4001, False)
-    golden_decode("decode_L64_K4", 64, 1, 1001, 4002, True)
-    golden_decode("decode_L64_N6_c2", 64, 1, 1001, 4003, False, use_c2=True)
-    golden_vq("vq_20000", 20000, 5001)
-    golden_ic_large_angle("ic_large_angle_L48", 48, 6001)
-    golden_training_losses("training_losses_B6", 6, 24, 7001)
-    golden_sample_qualities("sample_qualities_exact", 40, 2, 8001, 0.0)
-    golden_sample_qualities("sample_qualities_noisy", 40, 3, 8002, 0.08)
+    names = sys.argv[1:] or list(GOLDENS)
+    if "decode_L64_N6_c2" in names or not sys.argv[1:]:
+        export_c2_decoder()
+    for n in names:
+        GOLDENS[n](n)
 
 
 if __name__ == "__main__":

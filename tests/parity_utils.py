@@ -38,6 +38,17 @@ def denoiser_case(meta, lengths=None):
     return dict(X=X, cg_z=z, mask=mask, x=x, t=t, k_neighbors=k_nb)
 
 
+def members_case(meta):
+    """Rebuild the inputs of oracle/make_goldens.golden_denoiser_members: ONE frame, `members` batch rows on it."""
+    L, members, k_nb, prot_seed, x_seed = (int(v) for v in meta[:5])
+    t = torch.tensor([int(v) for v in meta[5:]], dtype=torch.int64)
+    prot = synthetic.make_protein(L, 1, seed=prot_seed)
+    X = prot.ca_full[:, 1:-1].contiguous()                      # [1, L, 3]
+    z = prot.restype_full[1:-1][None].contiguous()              # [1, L]
+    x = synthetic.latent_noise((members, L, 3), x_seed)
+    return dict(prot=prot, X=X, cg_z=z, x=x, t=t, k_neighbors=k_nb, members=members, L=L)
+
+
 def knn_tie_aware_equal(idx_a, idx_b, d_ref, valid_rows=None):
     """idx_* [R,K] integer arrays, d_ref [R,K] the reference's sorted distances for those rows."""
     idx_a, idx_b, d_ref = (np.asarray(v) for v in (idx_a, idx_b, d_ref))

@@ -181,7 +181,7 @@ def test_sampler_100_steps_f16_tier(eng, denoiser):
     plan.sample(x, nz, use_graph=False)
     err = P.rel_err(x.cpu(), g["sample_0"])
     print(f"f16 tier, 100 steps: latent rel err {err:.3e}")
-    assert err < 1e-2
+    assert err < 2e-3                                   # measured 5.6e-4
     xg = z0.cuda().clone()
     plan.sample(xg, nz, use_graph=True)
     assert torch.equal(xg, x)
@@ -208,8 +208,8 @@ def test_full_path_f16_tier_stagewise(eng, R):
     lat_err = P.rel_err(res["f16"]["latent"], res["fp32"]["latent"])
     flips = float((res["f16"]["idx"] != res["fp32"]["idx"]).float().mean())
     print(f"f16 vs fp32 tier: latent rel err {lat_err:.3e}, end-to-end VQ code flip rate {flips:.4f}")
-    assert lat_err < 1e-2
-    assert flips < 0.05
+    assert lat_err < 2e-3                               # measured ~6e-4
+    assert flips <= 0.005                               # measured 0 (at most 2 of 480 codes)
     # (iii)/(iv): decode the f16-tier latent with the CPU oracle: indices exact, coordinates within tolerance
     mean, std = (torch.tensor(v) for v in weights.LATENT_STATS[("N6", "PED")])
     mask = torch.ones(ENS, 120, dtype=torch.bool)
@@ -324,7 +324,8 @@ def _decode_case(eng, g, angle, c2, ens=1):
 
 
 @pytest.mark.parametrize("name,angle,c2", [("decode_L64_N6", False, False), ("decode_L64_K4", True, False),
-                                           ("decode_L64_N6_c2", False, True)])
+                                           ("decode_L64_N6_c2", False, True), ("decode_c2_L300_N6", False, False),
+                                           ("decode_c4_L2000_K4", True, False)])
 def test_decode_vs_oracle_and_golden(eng, R, denoiser, name, angle, c2):
     _, den = denoiser
     g = P.golden(name)
@@ -422,7 +423,7 @@ def test_reference_call_surface_end_to_end(R):
     zz = prot.restype_full[1:-1][None].expand(Fr, -1)
     ref_lat = R.sample_loop(dsd, z, X, zz, mask, noises, R.respaced_schedule(T))
     assert P.rel_err(first.cpu(), ref_lat) < 1e-4
-    lat = get_norm_feature(first, "latent", True, False, norm_in=False, dataname="PED_N6")
+    lat = get_norm_feature(first, "N6", norm_channel=True, norm_single=False, norm_in=False, dataname="PED")   # test.py:548
     mean, std = (torch.tensor(v) for v in weights.LATENT_STATS[("N6", "PED")])
     assert torch.equal(lat.cpu(), first.cpu() * std + mean)
     zq, idx, loss = vae.quantize(lat, mask=mask.cuda())
@@ -451,6 +452,132 @@ def test_module_forward_matches_oracle_ragged_batch(R):
     m = c["mask"] & torch.tensor([True, True])[:, None]
     m[1] = False                                       # rows of the shorter protein see topk's arbitrary tie order in the reference
     assert np.abs(out.numpy() - g["out"])[m.numpy()].max() < 5e-5
+
+
+# --------------------------------------------------------------------------------------- parity AT the BASELINE.json shapes
+def _members_plan(eng, c, precision):
+    den = eng.DenoiserEngine(weights.init_denoiser_state(0), c["k_neighbors"])
+    plan = eng.Plan(den, 1, c["members"], c["L"], precision)
+    plan._keep = den
+    plan.set_frames(c["X"], torch.tensor([c["L"]]), c["cg_z"].int(), torch.zeros(c["members"], dtype=torch.int32))
+    return plan
+
+
+@pytest.mark.parametrize("name", ["denoiser_c2_L300x10", "denoiser_c4_L2000_K48x2"])
+@pytest.mark.parametrize("precision,rel_bar,abs_bar", [("fp32", 2e-5, 5e-5), ("f16", 1.5e-3, 6e-3)])
+def test_denoiser_forward_at_baseline_shapes_vs_reference(eng, name, precision, rel_bar, abs_bar):
+    """configs[1] (one 300-residue frame x 10 members, t from 999 to 0) and configs[3] (2000 residues, k = 48, 2 members): one
+    forward of BOTH tiers against the output of the unmodified reference (tests/golden, oracle/make_goldens.py).
+    Bars: fp32 tier 5e-5 max-abs; f16 tier 1.5e-3 relative / 6e-3 max-abs on O(1) outputs (measured ~4e-4 / ~2e-3)."""
+    g = P.golden(name)
+    c = P.members_case(g["meta"])
+    plan = _members_plan(eng, c, precision)
+    K = plan.K
+    assert P.knn_tie_aware_equal(plan.buffer("nbr_idx").cpu().numpy().reshape(-1, K)[::8], g["E_idx"].reshape(-1, K).astype(np.int64)[::8],
+                                 g["D_nb"].reshape(-1, K))
+    out = plan.forward(c["x"].cuda(), c["t"].float().cuda()).cpu()
+    ref = torch.from_numpy(g["out"])
+    rel, mx = P.rel_err(out, ref), float((out - ref).abs().max())
+    print(f"{name} {precision}: rel {rel:.3e} max-abs {mx:.3e}")
+    assert rel < rel_bar and mx < abs_bar
+
+
+@pytest.mark.parametrize("precision,rel_bar,abs_bar", [("fp32", 2e-5, 5e-5), ("f16", 1.5e-3, 6e-3)])
+def test_denoiser_forward_c3_shape_vs_reference(eng, denoiser, precision, rel_bar, abs_bar):
+    """configs[2]-shaped: three 500-residue frames, one member each."""
+    _, den = denoiser
+    g = P.golden("denoiser_c3_L500_B3")
+    c = P.denoiser_case(g["meta"])
+    plan = _plan_for_case(eng, den, c, precision=precision, keep_debug=False)
+    out = plan.forward(c["x"].cuda(), c["t"].float().cuda()).cpu()
+    ref = torch.from_numpy(g["out"])
+    rel, mx = P.rel_err(out, ref), float((out - ref).abs().max())
+    print(f"denoiser_c3_L500_B3 {precision}: rel {rel:.3e} max-abs {mx:.3e}")
+    assert rel < rel_bar and mx < abs_bar
+
+
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-4), ("f16", 5e-3)])
+def test_sampler_5_steps_at_c2_shape_vs_reference(eng, precision, bar):
+    """5-step p_sample_loop of 10 members on the 300-residue frame (graph and eager) against the reference's own loop."""
+    from codlad_b200.diffusion import create_diffusion
+    g = P.golden("sampler_c2_L300x10_5")
+    L, members, prot_seed, z_seed, noise_seed, steps = (int(v) for v in g["meta"])
+    c = dict(P.members_case([L, members, 64, prot_seed, 0]))
+    plan = _members_plan(eng, c, precision)
+    diff = create_diffusion(str(steps))
+    assert np.array_equal(np.array(diff.timestep_map), g["timestep_map"])
+    plan.set_schedule(diff.timestep_map, diff.coef_table())
+    z0 = synthetic.latent_noise((members, L, 3), z_seed).cuda()
+    nz = synthetic.latent_noise((steps, members, L, 3), noise_seed).cuda().contiguous()
+    x = plan.sample(z0.clone(), nz, use_graph=False)
+    err = P.rel_err(x.cpu(), g["sample_0"])
+    print(f"sampler_c2_L300x10_5 {precision}: rel {err:.3e}")
+    assert err < bar
+    xg = plan.sample(z0.clone(), nz, use_graph=True)
+    assert torch.equal(xg, x)
+
+
+# --------------------------------------------------------------------------------------- plan re-use hazards (ADVICE round 1)
+def test_module_plan_cache_follows_batch_content():
+    """Two different batches of the same shape in sequence, the first freed (the reference driver loop, test.py:481-534): the
+    module must not serve the second batch from the plan built for the first (round-1 bug: cache keyed on data_ptr)."""
+    import gc
+    from codlad_b200.latent_model import MPNN_models
+    model = MPNN_models["mpnn_diffusion"](precision="fp32")
+    model.load_state_dict(weights.init_denoiser_state(0))
+    L = 40
+    x = synthetic.latent_noise((1, L, 3), 3).cuda()
+    t = torch.tensor([500.0]).cuda()
+    mask = torch.ones(1, L, dtype=torch.bool).cuda()
+    outs, solo = [], []
+    for seed in (31, 32, 33, 34):
+        batch = {k: v.cuda() if torch.is_tensor(v) else v for k, v in synthetic.collate(synthetic.make_protein(L, 1, seed=seed)).items()}
+        outs.append(model(x, t, None, mask=mask, batch=batch).cpu())
+        del batch
+        gc.collect()
+        torch.cuda.empty_cache()
+    for seed in (31, 32, 33, 34):
+        fresh = MPNN_models["mpnn_diffusion"](precision="fp32")
+        fresh.load_state_dict(weights.init_denoiser_state(0))
+        solo.append(fresh(x, t, None, mask=mask, batch=synthetic.collate(synthetic.make_protein(L, 1, seed=seed))).cpu())
+    for a, b in zip(outs, solo):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[0], outs[1])
+    # in-place edit of the coordinates of a live batch is seen too (version counter / content check)
+    batch = synthetic.collate(synthetic.make_protein(L, 1, seed=31))
+    a = model(x, t, None, mask=mask, batch=batch).cpu()
+    batch["CG_nxyz"][:, 1:] += 0.25 * torch.randn(L, 3, generator=torch.Generator().manual_seed(1))
+    assert not torch.equal(model(x, t, None, mask=mask, batch=batch).cpu(), a)
+
+
+def test_graph_follows_the_mask_geometry(eng, denoiser):
+    """A full-length frame set, then a ragged one of the same padded shape, then full again, sampled through ONE plan with
+    use_graph=True: the graph must be re-captured when the masked / unmasked kernel choice changes (round-1 bug: the
+    unmasked message kernel was replayed on ragged frames)."""
+    from codlad_b200.diffusion import create_diffusion
+    _, den = denoiser
+    L, T = 72, 6
+    diff = create_diffusion(str(T))
+    full = P.denoiser_case([L, 2, 64, 1501, 1, 0, 0])
+    ragged = P.denoiser_case([L, 0, 64, 1502, 1, 0, 0], [L, 50])
+    z0 = synthetic.latent_noise((2, L, 3), 4).cuda()
+    nz = synthetic.latent_noise((T, 2, L, 3), 5).cuda().contiguous()
+    plan = eng.Plan(den, 2, 2, L, "f16")
+    plan.set_schedule(diff.timestep_map, diff.coef_table())
+    x, noise = torch.empty_like(z0), nz
+    res = {}
+    for tag, c in (("full", full), ("ragged", ragged), ("full2", full)):
+        plan.set_frames(c["X"], c["mask"].sum(1).int(), c["cg_z"].int(), torch.arange(2, dtype=torch.int32))
+        x.copy_(z0)
+        plan.sample(x, noise, use_graph=True)
+        res[tag] = x.clone()
+        fresh = eng.Plan(den, 2, 2, L, "f16")
+        fresh.set_schedule(diff.timestep_map, diff.coef_table())
+        fresh.set_frames(c["X"], c["mask"].sum(1).int(), c["cg_z"].int(), torch.arange(2, dtype=torch.int32))
+        want = fresh.sample(z0.clone(), nz, use_graph=False)
+        valid = c["mask"].cuda()
+        assert torch.equal(res[tag][valid], want[valid]), tag
+    assert torch.equal(res["full"], res["full2"])
 
 
 # --------------------------------------------------------------------------------------- BASELINE configs[2] / [3] shapes

@@ -98,7 +98,57 @@ def test_reference_surface_modules_have_reference_state_dict_keys():
         assert list(v.state_dict().keys()) == list(weights.vae_decode_shapes(angle).keys())
     import torch
     x = torch.randn(2, 5, 3)
-    assert torch.allclose(get_norm_feature(get_norm_feature(x, norm_in=False, dataname="Atlas_K4"), norm_in=True, dataname="Atlas_K4"), x, atol=1e-5)
+    # reference call form (test.py:548 / train_latent.py:194): feature_type = VAE type, dataname = data set; IDRome_test_7 is remapped
+    y = get_norm_feature(x, "K4", norm_channel=True, norm_single=False, norm_in=False, dataname="Atlas")
+    mean, std = (torch.tensor(v) for v in weights.LATENT_STATS[("K4", "Atlas")])
+    assert torch.equal(y, x * std + mean)
+    assert torch.allclose(get_norm_feature(y, "K4", norm_in=True, dataname="Atlas"), x, atol=1e-5)
+    assert torch.equal(get_norm_feature(x, "N6", norm_in=False, dataname="IDRome_test_7"), get_norm_feature(x, "N6", norm_in=False, dataname="PED"))
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        get_norm_feature(x, "PED", norm_in=False, dataname="PED")          # the reference would fail to open PED_PED_x_mean.pt
+    with pytest.raises(NotImplementedError):
+        get_norm_feature(x, "N6", norm_single=True, norm_in=False, dataname="PED")
+    # VAE.load_state_dict is strict on the decode-side tensors (a mismatched checkpoint must not decode with random weights),
+    # ignores encoder extras and strips a DDP prefix
+    v = VAE("N6")
+    good = {"module." + k: t.clone() for k, t in weights.init_vae_decode_state(1).items()}
+    good["module.encoder.some.weight"] = torch.zeros(3)
+    v.load_state_dict(good)
+    assert torch.equal(v.state_dict()["map_out.weight"], good["module.map_out.weight"])
+    bad = dict(good)
+    bad.pop("module.map_out.weight")
+    with pytest.raises(RuntimeError):
+        v.load_state_dict(bad)
+    v.load_state_dict(bad, strict=False)
+
+
+def test_batching_matches_reference_padding_and_make_directed():
+    """pad_frames == reshape_and_create_mask's padding (models/gcn_nn.py:35-43); batch_csr == make_directed (:54-64) grouped by
+    padded source row with frame-local, ascending neighbour ids."""
+    import torch
+    from codlad_b200 import batching, synthetic
+    prots = [synthetic.make_protein(n, 1, seed=70 + i) for i, n in enumerate([12, 30, 7])]
+    batch = synthetic.collate_many(prots)
+    num = batch["num_CGs"]
+    L = int(num.max())
+    X, z = batching.pad_frames(batch["CG_nxyz"], num)
+    ref = torch.nn.utils.rnn.pad_sequence(torch.split(batch["CG_nxyz"], num.tolist(), dim=0), batch_first=True)
+    assert torch.equal(X, ref[..., 1:]) and torch.equal(z.float(), ref[..., 0])
+    row_ptr, col = batching.batch_csr(batch["CG_nbr_list"], num, L)
+    nbr = torch.cat([batch["CG_nbr_list"], batch["CG_nbr_list"].flip(1)], 0)          # undirected (i<j) input -> both directions
+    off = torch.cumsum(num, 0) - num
+    want = {}
+    for a, b in nbr.tolist():
+        f = int(torch.bucketize(torch.tensor(a), torch.cumsum(num, 0), right=True))
+        want.setdefault(f * L + a - int(off[f]), []).append(b - int(off[f]))
+    for r in range(len(prots) * L):
+        got = col[int(row_ptr[r]):int(row_ptr[r + 1])].tolist()
+        assert got == sorted(want.get(r, [])), r
+    # an already directed list is taken as is
+    rp2, col2 = batching.batch_csr(nbr, num, L)
+    assert torch.equal(rp2, row_ptr) and torch.equal(col2, col)
+    assert batching.batch_csr(torch.zeros(0, 2, dtype=torch.int64), num, L)[0].numel() == len(prots) * L + 1
 
 
 def test_p_mean_variance_matches_oracle_update():

@@ -41,6 +41,47 @@ def test_denoiser_forward(name, lengths):
     assert np.abs(out.numpy() - g["out"])[m.numpy()].max() < 2e-5
 
 
+# ---- BASELINE.json shapes: configs[1] (300 x 10 members), configs[2] (500-residue proteins), configs[3] (2000 residues, k = 48)
+@pytest.mark.parametrize("name", ["denoiser_c2_L300x10", "denoiser_c4_L2000_K48x2"])
+def test_denoiser_forward_members_at_baseline_shapes(name):
+    g = P.golden(name)
+    c = P.members_case(g["meta"])
+    sd = weights.init_denoiser_state(0)
+    nb, L = c["members"], c["L"]
+    torch.set_num_threads(8)
+    graph = R.edge_embedding(sd, c["X"], torch.ones(1, L, dtype=torch.int32), c["k_neighbors"])
+    K = graph[0].shape[-1]
+    assert P.knn_tie_aware_equal(graph[0].reshape(-1, K).numpy()[::8], g["E_idx"].reshape(-1, K).astype(np.int64)[::8], g["D_nb"].reshape(-1, K))
+    exp = lambda v: v.expand(nb, *v.shape[1:]).contiguous()
+    out = R.denoiser_forward(sd, c["x"], c["t"], exp(c["X"]), exp(c["cg_z"]), torch.ones(nb, L, dtype=torch.bool), c["k_neighbors"],
+                             graph=(exp(graph[0]), exp(graph[3])))
+    assert np.abs(out.numpy() - g["out"]).max() < 3e-5
+
+
+def test_denoiser_forward_c3_shape():
+    g = P.golden("denoiser_c3_L500_B3")
+    c = P.denoiser_case(g["meta"])
+    sd = weights.init_denoiser_state(0)
+    torch.set_num_threads(8)
+    out = R.denoiser_forward(sd, c["x"], c["t"], c["X"], c["cg_z"], c["mask"], c["k_neighbors"])
+    assert np.abs(out.numpy() - g["out"]).max() < 3e-5
+
+
+def test_sampler_members_5_steps_c2_shape():
+    g = P.golden("sampler_c2_L300x10_5")
+    L, members, prot_seed, z_seed, noise_seed, steps = (int(v) for v in g["meta"])
+    sch = R.respaced_schedule(steps)
+    assert np.array_equal(sch["timestep_map"], g["timestep_map"])
+    sd = weights.init_denoiser_state(0)
+    prot = synthetic.make_protein(L, 1, seed=prot_seed)
+    X = prot.ca_full[:, 1:-1].expand(members, -1, -1).contiguous()
+    z = prot.restype_full[1:-1][None].expand(members, -1).contiguous()
+    torch.set_num_threads(8)
+    final = R.sample_loop(sd, synthetic.latent_noise((members, L, 3), z_seed), X, z, torch.ones(members, L, dtype=torch.bool),
+                          synthetic.latent_noise((steps, members, L, 3), noise_seed), sch)
+    assert P.rel_err(final, g["sample_0"]) < 1e-4
+
+
 def test_diffusion_schedule_and_sampler():
     g = P.golden("sampler_L64_100")
     L, prot_seed, z_seed, noise_seed, steps = (int(v) for v in g["meta"])
@@ -61,7 +102,8 @@ def test_diffusion_schedule_and_sampler():
 
 
 @pytest.mark.parametrize("name,angle,c2", [("decode_L64_N6", False, False), ("decode_L64_K4", True, False),
-                                           ("decode_L64_N6_c2", False, True)])
+                                           ("decode_L64_N6_c2", False, True), ("decode_c2_L300_N6", False, False),
+                                           ("decode_c4_L2000_K4", True, False)])
 def test_decode(name, angle, c2):
     g = P.golden(name)
     L, frames, prot_seed, lat_seed, _ = (int(v) for v in g["meta"])

@@ -1,4 +1,4 @@
-"""Needs a trace build: bash scratch/build_variant.sh trace -DCB2_TRACE_CTRL [-DCB2_TRACE_EPI]; CB2_LIB=codlad_b200/_variants/lib_trace.so"""
+"""Needs a trace build: bash tools/dev/build_variant.sh trace -DCB2_TRACE_CTRL [-DCB2_TRACE_EPI]; CB2_LIB=codlad_b200/_variants/lib_trace.so"""
 import sys, torch
 sys.path.insert(0, '.')
 from codlad_b200 import synthetic, engine, weights
