@@ -43,6 +43,7 @@ SIGNATURES = {
     "cb2_plan_decode": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "cb2_plan_buffer": (_I, [_P, C.c_char_p, _P, _LL, _P]),
     "cb2_plan_run_edge_kernel": (_I, [_P, _I, _I, _P]),
+    "cb2_plan_run_stage": (_I, [_P, _P, _I, _I, _P, _P]),
     "cb2_knn_topk": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "cb2_vq_lookup": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "cb2_p_sample": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),

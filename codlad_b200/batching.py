@@ -55,3 +55,18 @@ def batch_csr(nbr: torch.Tensor, num: torch.Tensor, L: int):
     row_ptr = torch.zeros(F * L + 1, dtype=torch.int64)
     row_ptr[1:] = torch.cumsum(counts, 0)
     return row_ptr.to(torch.int32), dst[order].to(torch.int32)
+
+
+def merge_batches(batches):
+    """Concatenate reference-schema batch dicts (one or more frames each) the way CG_collate does
+    (utils/dataset_module.py:259-295): rows concatenated, CG_nbr_list shifted by the running residue count."""
+    out, nbrs, off = {}, [], 0
+    for b in batches:
+        nbrs.append(b["CG_nbr_list"] + off)
+        off += int(b["num_CGs"].sum())
+    for k in batches[0]:
+        if k == "CG_nbr_list":
+            out[k] = torch.cat(nbrs, 0)
+        elif torch.is_tensor(batches[0][k]):
+            out[k] = torch.cat([b[k] for b in batches], 0)
+    return out

@@ -729,6 +729,36 @@ int cb2_plan_run_edge_kernel(cb2_plan* h, int mode, int layer, void* stream) {
     return edge_dispatch(h->p, mode, layer, h->p.mod, 0, (cudaStream_t)stream);
 }
 
+int cb2_plan_run_stage(cb2_plan* h, const cb2_vae* v, int stage, int layer, float* xyz_scratch, void* stream) {
+    if (!h || stage < 0 || stage > 9) { set_error("run_stage: bad argument"); return 1; }
+    Plan& p = h->p;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->frames_ready) { set_error("run_stage: set_frames first"); return 1; }
+    if (stage <= 3 && (p.coef_steps <= 0 || !p.model)) { set_error("run_stage: set_schedule first"); return 1; }
+    if (stage >= 6 && (!h->topo_ready || !v)) { set_error("run_stage: set_topology first (and pass the vae)"); return 1; }
+    const int N = p.NB * p.L;
+    switch (stage) {
+        case 0: case 1: case 2:
+            if (layer < 0 || layer > 2) { set_error("run_stage: layer"); return 1; }
+            return edge_dispatch(p, stage, layer, p.mod, 0, s);
+        case 3: {
+            if (layer < 0 || layer > 5) { set_error("run_stage: phase"); return 1; }
+            const bool last = layer == 5, tc = p.precision == PREC_F16 && p.node_tc != nullptr;
+            const float *xt = last ? h->xa : nullptr, *nz = last ? h->xa : nullptr, *cf = last ? p.coef : nullptr;
+            float* xn = last ? h->xb : nullptr;
+            return tc ? launch_node_update_tc(p, layer, p.mod, 0, xt, nz, xn, cf, s) : launch_node_update(p, layer, p.mod, 0, xt, nz, xn, cf, s);
+        }
+        case 4: return launch_knn(p.X, p.lengths, p.F, p.L, p.K, p.nbr_dist, p.nbr_idx, s);
+        case 5: return launch_edge_features(*p.model, p.X, p.lengths, p.nbr_idx, p.nbr_dist, p.F, p.L, p.K, p.E_dbg, p.hE0, p.precision, s);
+        case 6: return launch_vq_lookup(v->v, h->xa, N, p.L, p.lengths, p.frame_of, 1, h->vq_idx, h->zq, h->S40, s);
+        case 7: return launch_ic_decoder(v->v, h->S40, h->phi, N, p.L, p.frame_of, p.lengths, p.cg_z, h->csr_row, h->csr_col, h->E, h->edge_w, h->ic, s, &p.launches);
+        case 8:
+            if (!xyz_scratch) { set_error("run_stage: ic_to_xyz needs xyz_scratch"); return 1; }
+            return launch_ic_to_xyz(h->ca_full, h->ic, N, p.L, p.frame_of, p.lengths, h->orders, h->slot_atom, h->out_off, xyz_scratch, nullptr, s);
+        default: return launch_ic_edge_filters(v->v, p.X, p.F, p.L, h->csr_row, h->csr_col, h->E, h->edge_w, s);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- stand-alone kernels
 int cb2_knn_topk(const float* X, const int* lengths, int F, int L, int K, float* D, int* idx, void* stream) {
     if (!X || !D || !idx) { set_error("knn_topk: null argument"); return 1; }

@@ -61,6 +61,7 @@ struct TcParams {
     const __half* mod16;             // ENC_EDGE: [rows, 3, 256] gate (1 + scale) | gate * shift; member row at b * mod16_stride
     int mod16_stride;
     const __half* res;               // ENC_EDGE: residual source (= the tile's input rows)
+    __half* out;                     // ENC_EDGE: h_E rows written by the warpgroup version (the first version stores through TMA)
     const int *lengths, *frame_of, *nbr_idx;
     float* S;                        // [N, 128] neighbour sums (ENC_NODE / DEC)
     unsigned long long* trace;       // debug: stage timestamps of CTA 0 (nullptr = off)
@@ -648,6 +649,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     if (tid >= EPI_THREADS && tid < EPI_THREADS + 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+}  // namespace
+}  // namespace cb2
+// The warpgroup-per-tile variant of these kernels (edge_wg.cuh) was built and measured in round 2 and is slower at every shape
+// ("warpgroup variant"); it is compiled only into experiment builds (tools/dev/build_variant.sh -DCB2_WITH_WG,
+// selected at run time with CB2_EDGE_WG=1), never into the product library.
+namespace cb2 {
+namespace {
+#ifdef CB2_WITH_WG
+#include "edge_wg.cuh"
+#endif
+
 size_t tc_smem_bytes(int mode) {
     const int n_w = mode == EDGE_ENC_EDGE ? 3 : 2;
     return (size_t)(n_w + 4) * TILE_BYTES + (mode == EDGE_ENC_EDGE ? 0 : IND_BYTES) + 29 * 8 + 16;
@@ -683,6 +695,13 @@ int edge_tc_prepare(Plan& p) {
     CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_DEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_DEC)));
     CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_DEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_DEC)));
     CB2_CUDA(cudaFuncSetAttribute(edge_tc_kernel<EDGE_ENC_EDGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(EDGE_ENC_EDGE)));
+#ifdef CB2_WITH_WG
+    CB2_CUDA(cudaFuncSetAttribute(wg::edge_wg_kernel<EDGE_ENC_NODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::wg_smem_bytes(EDGE_ENC_NODE)));
+    CB2_CUDA(cudaFuncSetAttribute(wg::edge_wg_kernel<EDGE_ENC_NODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::wg_smem_bytes(EDGE_ENC_NODE)));
+    CB2_CUDA(cudaFuncSetAttribute(wg::edge_wg_kernel<EDGE_DEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::wg_smem_bytes(EDGE_DEC)));
+    CB2_CUDA(cudaFuncSetAttribute(wg::edge_wg_kernel<EDGE_DEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::wg_smem_bytes(EDGE_DEC)));
+    CB2_CUDA(cudaFuncSetAttribute(wg::edge_wg_kernel<EDGE_ENC_EDGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg::wg_smem_bytes(EDGE_ENC_EDGE)));
+#endif
     return 0;
 }
 
@@ -722,12 +741,28 @@ int launch_edge_tc(Plan& p, int mode, int layer, const float* mod_base, int mod_
         tp.mod16 = p.mod16 + row0 * 768 + layer * 256;
         tp.mod16_stride = mod_stride_b ? 768 : 0;
         tp.res = reinterpret_cast<const __half*>(first ? p.hE0 : p.hE);
+        tp.out = reinterpret_cast<__half*>(p.hE);
     } else {
         const DecLayerW& d = m.dec[layer];
         tp.P16 = p.P16[0]; tp.n_w = 2;
         tp.w_row[0] = row_of(d.W1b2_h); tp.w_row[1] = row_of(d.W2_h); tp.b2h = d.b2_16;
     }
     const int grid = min(p.num_sms, tp.n_tiles);
+#ifdef CB2_WITH_WG
+    static const bool wg_impl = getenv("CB2_EDGE_WG") != nullptr;        // A/B switch of experiment builds: the warpgroup-per-tile variant
+    if (wg_impl) {
+        const dim3 g(grid), b(wg::WG_CTA_THREADS);
+        const size_t sm = wg::wg_smem_bytes(mode);
+        if (mode == EDGE_ENC_EDGE) CB2_CUDA(launch_pdl(wg::edge_wg_kernel<EDGE_ENC_EDGE, false>, g, b, sm, s, maps, tp));
+        else if (mode == EDGE_ENC_NODE && masked) CB2_CUDA(launch_pdl(wg::edge_wg_kernel<EDGE_ENC_NODE, true>, g, b, sm, s, maps, tp));
+        else if (mode == EDGE_ENC_NODE) CB2_CUDA(launch_pdl(wg::edge_wg_kernel<EDGE_ENC_NODE, false>, g, b, sm, s, maps, tp));
+        else if (masked) CB2_CUDA(launch_pdl(wg::edge_wg_kernel<EDGE_DEC, true>, g, b, sm, s, maps, tp));
+        else CB2_CUDA(launch_pdl(wg::edge_wg_kernel<EDGE_DEC, false>, g, b, sm, s, maps, tp));
+        CB2_LAUNCH_CHECK();
+        p.launches++;
+        return 0;
+    }
+#endif
     const dim3 g(grid), b(CTA_THREADS);
     const size_t sm = tc_smem_bytes(mode);
     if (mode == EDGE_ENC_EDGE) CB2_CUDA(launch_pdl(edge_tc_kernel<EDGE_ENC_EDGE, false>, g, b, sm, s, maps, tp));

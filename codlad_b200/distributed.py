@@ -12,6 +12,32 @@ def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def init_from_env(backend: str = "nccl", local_rank: int = 0):
+    """Join the job torchrun (or the driver) started: one process per GPU, rendezvous from MASTER_ADDR / MASTER_PORT.  A
+    single-process run (WORLD_SIZE unset or 1) does not create a process group."""
+    import torch.distributed as dist
+    rank, world, _ = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        kw = {"device_id": torch.device("cuda", local_rank)} if backend == "nccl" else {}
+        dist.init_process_group(backend, **kw)
+    return rank, world
+
+
+def barrier():
+    """Launch barrier + device drain (both sides of every timed region)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def shutdown():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def shard_bounds(n_units: int, rank: int, world: int):
     """Contiguous balanced partition: rank r owns units [lo, hi); sizes differ by at most one."""
     base, extra = divmod(n_units, world)

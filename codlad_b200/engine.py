@@ -155,6 +155,11 @@ class Plan:
         """Measurement hook: one per-edge kernel on the current state (0 enc node msg, 1 enc edge update, 2 dec msg)."""
         N.check(N.lib().cb2_plan_run_edge_kernel(self.handle, int(mode), int(layer), N.stream_ptr()), "run_edge_kernel")
 
+    def run_stage(self, stage: int, layer: int = 0, vae: "VaeEngine | None" = None, xyz_scratch=None):
+        """Measurement hook: one stage of the path on the plan's buffers (see cb2_plan_run_stage in include/codlad_b200.h)."""
+        N.check(N.lib().cb2_plan_run_stage(self.handle, vae.handle if vae is not None else None, int(stage), int(layer),
+                                           N.dptr(xyz_scratch) if xyz_scratch is not None else None, N.stream_ptr()), "run_stage")
+
     # -- decode ----------------------------------------------------------------------------------
     def decode(self, vae: VaeEngine, latent, denorm: bool, num_atoms_total: int | None = None, want_ic: bool = True):
         latent = latent.to(self.device, torch.float32).contiguous()

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import batching, topology, weights
+from . import batching, distributed, topology, weights
 from .diffusion import create_diffusion
 from .engine import DenoiserEngine, Plan, VaeEngine
 
@@ -65,10 +65,11 @@ class FrameSet:
     def NB(self): return self.frame_of.numel()
 
 
-def frames_from_batch(batch: dict, infos, num_ensemble: int = 1) -> FrameSet:
+def frames_from_batch(batch: dict, infos, num_ensemble: int = 1, frame_of=None) -> FrameSet:
     """Convert a reference-schema batch dict (CG_collate, utils/dataset_module.py:259-295) of F frames
     plus their `info` tuples (one per frame, or one shared) into a FrameSet with `num_ensemble`
-    members per frame (member order: ensemble-major, i.e. b = e*F + f)."""
+    members per frame (member order: ensemble-major, i.e. b = e*F + f), or with the explicit member list
+    `frame_of` [NB] (frame index of every member; frames may then carry different member counts)."""
     num = batch["num_CGs"].to(torch.int64).cpu()
     F, L = num.numel(), int(num.max())
     cg = batch["CG_nxyz"].cpu().to(torch.float32)
@@ -94,7 +95,9 @@ def frames_from_batch(batch: dict, infos, num_ensemble: int = 1) -> FrameSet:
             slot_atom[f, :n * 14] = topology.slot_to_atom_map(per_frame[f], n)
             num_atoms[f] = permute.numel()
     csr_row, csr_col = batching.batch_csr(batch["CG_nbr_list"], num, L)
-    frame_of = torch.arange(F, dtype=torch.int32).repeat(num_ensemble)
+    if frame_of is None:
+        frame_of = torch.arange(F, dtype=torch.int32).repeat(num_ensemble)
+    frame_of = torch.as_tensor(frame_of, dtype=torch.int32)
     return FrameSet(X, ca_full, cg_z, num.to(torch.int32), csr_row, csr_col, orders, slot_atom, num_atoms, frame_of)
 
 
@@ -102,8 +105,10 @@ class Backmapper:
     """CG trace -> all-atom ensemble: 100-step latent diffusion + VQ-VAE decode + IC reconstruction."""
 
     def __init__(self, denoiser_state: dict, vae_state: dict, vae_type: str = "N6", k_neighbors: int = 64,
-                 num_sampling_steps: int = 100, precision: str = "f16", latent_stats=None):
+                 num_sampling_steps: int = 100, precision: str = "f16", latent_stats=None, max_plans: int = 4):
         self.precision = precision
+        self.k_neighbors = int(k_neighbors)
+        self.max_plans = int(max_plans)
         self.denoiser = DenoiserEngine(denoiser_state, k_neighbors)
         stats = latent_stats or weights.LATENT_STATS[(vae_type, VAE_DATA[vae_type])]
         self.vae = VaeEngine(vae_state, stats[0], stats[1], angle_variant=vae_type in ("K3", "K4"))
@@ -117,9 +122,15 @@ class Backmapper:
         key = (fs.F, fs.NB, fs.L, keep_debug)
         plan = self._plans.get(key)
         if plan is None:
+            while len(self._plans) >= self.max_plans:              # a plan owns every buffer of its geometry: keep few of them
+                old = self._plans.pop(next(iter(self._plans)))
+                self._bufs.pop(id(old), None)
+                old.close()
             plan = Plan(self.denoiser, fs.F, fs.NB, fs.L, self.precision, keep_debug)
             plan.set_schedule(self.diffusion.timestep_map, self.diffusion.coef_table())
-            self._plans[key] = plan
+        else:
+            self._plans.pop(key)                                   # re-insert: most recently used last
+        self._plans[key] = plan
         return plan
 
     def upload(self, fs: FrameSet, keep_debug: bool = False) -> Plan:
@@ -163,3 +174,104 @@ class Backmapper:
         host.copy_(out["xyz"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return host
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def partition_units(lengths, num_ensemble: int, world: int, k_neighbors: int = 64):
+    """Units of the sampling job = (frame, ensemble member), all independent.  Returns, per rank, the
+    sorted list of (frame, member) it owns.  Cost of a unit ~ L * min(K, L) edges.  With at least one frame per rank whole
+    frames are dealt out (longest-processing-time first), so each frame's k-NN graph / edge features are built once; with
+    fewer frames than ranks the units themselves are dealt out and a frame's features are rebuilt on every rank that holds
+    one of its members (configs[1] / configs[3]: one frame, members over the GPUs)."""
+    F = len(lengths)
+    cost = [float(n) * min(int(k_neighbors), int(n)) for n in lengths]
+    if F >= world:
+        frames = distributed.shard_by_cost([c * num_ensemble for c in cost], world)
+        return [[(f, e) for f in fr for e in range(num_ensemble)] for fr in frames]
+    units = [(f, e) for f in range(F) for e in range(num_ensemble)]
+    parts = distributed.shard_by_cost([cost[f] for f, _ in units], world)
+    return [[units[i] for i in p] for p in parts]
+
+
+def group_by_length(frames, lengths, max_frames: int = 32, max_pad: float = 0.12):
+    """Frames of one rank -> groups that share a padded plan: longest first, a frame joins the current group while the
+    group stays within `max_frames` and its padding (Lmax * n - sum L) / sum L within `max_pad`."""
+    order = sorted(frames, key=lambda f: (-lengths[f], f))
+    groups, cur, tot = [], [], 0
+    for f in order:
+        if cur and (len(cur) >= max_frames or (lengths[cur[0]] * (len(cur) + 1) - (tot + lengths[f])) > max_pad * (tot + lengths[f])):
+            groups.append(cur)
+            cur, tot = [], 0
+        cur.append(f)
+        tot += lengths[f]
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+class ShardedBackmapper:
+    """The multi-GPU driver of the sampling job (the reference runs loops 1-4 of test.py:413-582 in one process on one
+    GPU): every rank holds the whole (host) input, takes its share of the (frame, member) units by cost, back-maps them
+    with its own `Backmapper`, and the coordinates are collected on rank 0's host.  No collective on the data path; the
+    only communication is that final point-to-point gather."""
+
+    def __init__(self, backmapper, rank: int | None = None, world: int | None = None, max_frames: int = 32, max_pad: float = 0.12):
+        r, w, _ = distributed.env_rank_world()
+        self.bm, self.rank, self.world = backmapper, (r if rank is None else rank), (w if world is None else world)
+        self.max_frames, self.max_pad = max_frames, max_pad
+
+    def plan(self, lengths, num_ensemble: int):
+        k = self.bm.k_neighbors if self.bm is not None else 64
+        return partition_units(lengths, num_ensemble, self.world, k)
+
+    def local_groups(self, units, lengths):
+        """[(frames of the group, frame_of [NB] local indices, [(frame, member)] in member order)] for this rank's units."""
+        by_frame = {}
+        for f, e in units:
+            by_frame.setdefault(f, []).append(e)
+        out = []
+        for frames in group_by_length(sorted(by_frame), lengths, self.max_frames, self.max_pad):
+            members = [(f, e) for f in frames for e in by_frame[f]]
+            members.sort(key=lambda fe: (fe[1], frames.index(fe[0])))              # ensemble-major like the single-GPU driver
+            out.append((frames, [frames.index(f) for f, _ in members], members))
+        return out
+
+    def backmap_local(self, batches, infos, units, lengths, generator=None):
+        """Back-map this rank's units: {(frame, member): host tensor [Na, 3]}."""
+        res = {}
+        for frames, frame_of, members in self.local_groups(units, lengths):
+            fs = frames_from_batch(batching.merge_batches([batches[f] for f in frames]), [infos[f] for f in frames], frame_of=frame_of).pin()
+            host = self.bm.backmap_host(fs, generator=generator)
+            for b, fe in enumerate(members):
+                o, na = int(fs.out_off[b]), int(fs.num_atoms[frame_of[b]])
+                res[fe] = host[o:o + na].clone()
+        return res
+
+    def backmap(self, batches, infos, num_ensemble: int, generator=None, _compute=None):
+        """batches: one reference-schema batch dict per frame (CG_collate of a single frame), infos: its `info` tuple.
+        Returns on rank 0 {(frame, member): [Na, 3]} for EVERY unit of the job, on the other ranks None."""
+        import torch.distributed as dist
+        lengths = [int(b["num_CGs"].sum()) for b in batches]
+        n_atoms = [int(i[0].numel()) for i in infos]
+        parts = self.plan(lengths, num_ensemble)
+        mine = (_compute or self.backmap_local)(batches, infos, parts[self.rank], lengths, generator) if parts[self.rank] else {}
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            return mine
+        flat = lambda units, res: torch.cat([res[u] for u in units], 0) if units else torch.zeros(0, 3)
+        if self.rank != 0:
+            if parts[self.rank]:
+                buf = flat(parts[self.rank], mine).contiguous()
+                dist.send(buf.cuda() if dist.get_backend() == "nccl" else buf, dst=0)
+            return None
+        out = dict(mine)
+        for r in range(1, self.world):
+            if not parts[r]:
+                continue
+            rows = sum(n_atoms[f] for f, _ in parts[r])
+            buf = torch.empty(rows, 3, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.recv(buf, src=r)
+            buf, o = buf.cpu(), 0
+            for f, e in parts[r]:
+                out[(f, e)] = buf[o:o + n_atoms[f]]
+                o += n_atoms[f]
+        return out

@@ -116,6 +116,15 @@ CB2_API int cb2_plan_buffer(cb2_plan* p, const char* name, void* dst, long long 
  * state.  mode 0 = encoder node message, 1 = encoder edge update, 2 = decoder message; layer 0..2. */
 CB2_API int cb2_plan_run_edge_kernel(cb2_plan* p, int mode, int layer, void* stream);
 
+/* Measurement hook (bench.py roofline_all): launches ONE stage of the path on the plan's current buffers, exactly as the
+ * step loop / the per-frame precompute / the decode launch it (results land in the plan's own buffers and are not meant to be
+ * read).  stage: 0-2 = per-edge kernels as above; 3 = node update of phase `layer` (0-2 encoder, 3-5 decoder, 5 includes
+ * FinalLayer + p_sample; reference protein_mpnn_utils.py:247-259,307-317); 4 = k-NN graph (:447-459); 5 = edge featuriser
+ * (:369-523); 6 = de-normalise + VQ lookup + map_out (vae_model.py:835); 7 = IC decoder (vae_model.py:467-503); 8 = ic_to_xyz
+ * (utils_ic.py:242-268, needs `xyz_scratch` of [total atoms, 3]); 9 = IC distance filters (gcn_nn.py:222-338).
+ * Stages 6-9 need cb2_plan_set_topology. */
+CB2_API int cb2_plan_run_stage(cb2_plan* p, const cb2_vae* v, int stage, int layer, float* xyz_scratch, void* stream);
+
 /* ---- stand-alone kernels (same code the plan uses) ---------------------------------------------- */
 
 /* Replaces: CA_ProteinFeatures._dist (protein_mpnn_utils.py:447-459).  D [F,L,K] fp32, idx [F,L,K] int32,
