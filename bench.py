@@ -435,6 +435,7 @@ def e2e_dropin(args, prot, batch, dev, steps):
     vae.load_state_dict(weights.init_vae_decode_state(0))
     diffusion = create_diffusion(str(T_STEPS))
     mb = synthetic.collate(prot, frames=[0] * ENSEMBLE)             # the ensemble as a batch of 10 copies of the frame (reference schema)
+    mb = {k: v.to(dev) if torch.is_tensor(v) else v for k, v in mb.items()}          # test.py:487 batch_to(batch, device)
     mask = torch.ones(ENSEMBLE, L_RES, dtype=torch.bool, device=dev)
     og = mb["OG_CG_nxyz"].reshape(-1, L_RES + 2, 4)
 

@@ -34,13 +34,15 @@ def pad_frames(cg_nxyz: torch.Tensor, num: torch.Tensor, L: int | None = None):
 
 def batch_csr(nbr: torch.Tensor, num: torch.Tensor, L: int):
     """CG_nbr_list [E, 2] with batch-global (ragged) node ids -> directed CSR over the F*L PADDED rows with
-    frame-local column ids sorted ascending: (row_ptr [F*L+1] int32, col [E'] int32).  An undirected list (only i<j or
-    only i>j pairs) is symmetrised first, exactly as make_directed does (reference models/gcn_nn.py:54-64)."""
-    num = num.to(torch.int64).cpu()
+    frame-local column ids sorted ascending: (row_ptr [F*L+1] int32, col [E'] int32), on the device of `nbr` (a list that
+    already lives on the GPU is converted there).  An undirected list (only i<j or only i>j pairs) is symmetrised first,
+    exactly as make_directed does (reference models/gcn_nn.py:54-64)."""
+    dev = nbr.device
+    num = num.to(dev, torch.int64)
     F = num.numel()
-    nbr = nbr.detach().to("cpu", torch.int64)
+    nbr = nbr.detach().to(torch.int64)
     if nbr.numel() == 0:
-        return torch.zeros(F * L + 1, dtype=torch.int32), torch.zeros(0, dtype=torch.int32)
+        return torch.zeros(F * L + 1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
     a, b = nbr[:, 0], nbr[:, 1]
     if not (bool((a > b).any()) and bool((b > a).any())):
         nbr = torch.cat([nbr, nbr.flip(1)], dim=0)
@@ -52,7 +54,7 @@ def batch_csr(nbr: torch.Tensor, num: torch.Tensor, L: int):
     row = frame * L + src
     order = torch.argsort(row * L + dst, stable=True)
     counts = torch.bincount(row, minlength=F * L)
-    row_ptr = torch.zeros(F * L + 1, dtype=torch.int64)
+    row_ptr = torch.zeros(F * L + 1, dtype=torch.int64, device=dev)
     row_ptr[1:] = torch.cumsum(counts, 0)
     return row_ptr.to(torch.int32), dst[order].to(torch.int32)
 

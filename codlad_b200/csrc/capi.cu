@@ -660,11 +660,11 @@ int cb2_plan_set_topology(cb2_plan* h, const cb2_vae* v, const float* ca_full, c
     }
     h->E = n_edges;
     CB2_CUDA(cudaMemcpyAsync(h->ca_full, ca_full, (size_t)p.F * (p.L + 2) * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    CB2_CUDA(cudaMemcpyAsync(h->csr_row, csr_row_ptr, (FL + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
-    if (n_edges) CB2_CUDA(cudaMemcpyAsync(h->csr_col, csr_col, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, s));
-    CB2_CUDA(cudaMemcpyAsync(h->orders, atom_orders, FL * 30, cudaMemcpyHostToDevice, s));
-    CB2_CUDA(cudaMemcpyAsync(h->slot_atom, slot_atom, FL * 14 * sizeof(int), cudaMemcpyHostToDevice, s));
-    CB2_CUDA(cudaMemcpyAsync(h->out_off, out_offset, p.NB * sizeof(long long), cudaMemcpyHostToDevice, s));
+    CB2_CUDA(cudaMemcpyAsync(h->csr_row, csr_row_ptr, (FL + 1) * sizeof(int), cudaMemcpyDefault, s));
+    if (n_edges) CB2_CUDA(cudaMemcpyAsync(h->csr_col, csr_col, (size_t)n_edges * sizeof(int), cudaMemcpyDefault, s));
+    CB2_CUDA(cudaMemcpyAsync(h->orders, atom_orders, FL * 30, cudaMemcpyDefault, s));
+    CB2_CUDA(cudaMemcpyAsync(h->slot_atom, slot_atom, FL * 14 * sizeof(int), cudaMemcpyDefault, s));
+    CB2_CUDA(cudaMemcpyAsync(h->out_off, out_offset, p.NB * sizeof(long long), cudaMemcpyDefault, s));
     if (!h->frames_ready) { set_error("set_topology: call cb2_plan_set_frames first (needs X)"); return 1; }
     if (int e = launch_ic_edge_filters(v->v, p.X, p.F, p.L, h->csr_row, h->csr_col, n_edges, h->edge_w, s)) return e;
     p.launches += 1;

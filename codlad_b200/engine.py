@@ -111,11 +111,13 @@ class Plan:
     def set_topology(self, vae: VaeEngine, ca_full, csr_row, csr_col, orders, slot_atom, out_off):
         ca_full = ca_full.to(self.device, torch.float32, non_blocking=True).contiguous()
         assert ca_full.shape == (self.F, self.L + 2, 3)
-        csr_row = csr_row.to(torch.int32).cpu().contiguous()
-        csr_col = csr_col.to(torch.int32).cpu().contiguous()
-        orders = orders.to(torch.int8).cpu().contiguous()
-        slot_atom = slot_atom.to(torch.int32).cpu().contiguous()
-        out_off = out_off.to(torch.int64).cpu().contiguous()
+        # host or device tensors are both accepted (cudaMemcpyDefault): a batch dict that already lives on the GPU (test.py:487
+        # batch_to(device)) is converted on the GPU and never comes back to the host
+        csr_row = csr_row.to(torch.int32).contiguous()
+        csr_col = csr_col.to(torch.int32).contiguous()
+        orders = orders.to(torch.int8).contiguous()
+        slot_atom = slot_atom.to(torch.int32).contiguous()
+        out_off = out_off.to(torch.int64).contiguous()
         assert csr_row.numel() == self.F * self.L + 1 and orders.numel() == self.F * self.L * 30
         assert slot_atom.numel() == self.F * self.L * 14 and out_off.numel() == self.NB
         N.check(N.lib().cb2_plan_set_topology(self.handle, vae.handle, N.dptr(ca_full), csr_row.data_ptr(), csr_col.data_ptr(),

@@ -219,6 +219,7 @@ class ShardedBackmapper:
         r, w, _ = distributed.env_rank_world()
         self.bm, self.rank, self.world = backmapper, (r if rank is None else rank), (w if world is None else world)
         self.max_frames, self.max_pad = max_frames, max_pad
+        self._fs_cache = {}
 
     def plan(self, lengths, num_ensemble: int):
         k = self.bm.k_neighbors if self.bm is not None else 64
@@ -240,7 +241,16 @@ class ShardedBackmapper:
         """Back-map this rank's units: {(frame, member): host tensor [Na, 3]}."""
         res = {}
         for frames, frame_of, members in self.local_groups(units, lengths):
-            fs = frames_from_batch(batching.merge_batches([batches[f] for f in frames]), [infos[f] for f in frames], frame_of=frame_of).pin()
+            # the padded / CSR form of a group is input-format conversion: done once per group of frames (keyed on the very batch
+            # objects), not once per pass
+            key = (tuple(id(batches[f]) for f in frames), tuple(frame_of))
+            fs = self._fs_cache.get(key)
+            if fs is None:
+                fs = frames_from_batch(batching.merge_batches([batches[f] for f in frames]), [infos[f] for f in frames], frame_of=frame_of).pin()
+                if len(self._fs_cache) >= 64:
+                    self._fs_cache.pop(next(iter(self._fs_cache)))
+                self._fs_cache[key] = fs
+                fs._keep = [batches[f] for f in frames]          # the ids in the key stay valid while the entry lives
             host = self.bm.backmap_host(fs, generator=generator)
             for b, fe in enumerate(members):
                 o, na = int(fs.out_off[b]), int(fs.num_atoms[frame_of[b]])

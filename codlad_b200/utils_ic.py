@@ -7,6 +7,9 @@ from . import _native as N
 from . import topology
 
 
+_TOPO_CACHE = {}      # (id(permute), id(atom_idx), id(atom_orders), B, L) -> device tables (+ the info tuple, so the ids stay valid)
+
+
 def ic_to_xyz(CG_nxyz, ic_recon, info):
     """CG_nxyz [B, L+2, 4] (column 0 = residue type; the untrimmed C-alpha trace), ic_recon [B, L, 13, 3]
     (bond, angle, torsion), info = (permute, atom_idx, atom_orders [10, L, 3]) -> [B, Na, 3] on the CUDA device.
@@ -19,12 +22,20 @@ def ic_to_xyz(CG_nxyz, ic_recon, info):
     na = int(permute.numel())
     ca = CG_nxyz[..., 1:].to(dev, torch.float32).contiguous()
     ic = ic_recon.to(dev, torch.float32).reshape(B, L, 13, 3).contiguous()
-    # one topology shared by the B frames: replicate the (small) per-frame tables so one launch covers the batch
-    orders = atom_orders.permute(1, 0, 2).to(torch.int8).contiguous().to(dev)[None].expand(B, -1, -1, -1).contiguous()
-    slot = topology.slot_to_atom_map(info, L).to(dev)[None].expand(B, -1).contiguous()
-    frame_of = torch.arange(B, dtype=torch.int32, device=dev)
-    lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
-    out_off = (torch.arange(B, dtype=torch.int64) * na).to(dev)
+    # one topology shared by the B frames: replicate the (small) per-frame tables so one launch covers the batch; the device
+    # copies are kept per topology object (the reference driver passes the same info_dict entry for every frame of a protein)
+    key = (id(permute), id(atom_idx), id(atom_orders), B, L, str(dev))
+    ent = _TOPO_CACHE.get(key)
+    if ent is None:
+        orders = atom_orders.permute(1, 0, 2).to(torch.int8).contiguous().to(dev)[None].expand(B, -1, -1, -1).contiguous()
+        slot = topology.slot_to_atom_map(info, L).to(dev)[None].expand(B, -1).contiguous()
+        frame_of = torch.arange(B, dtype=torch.int32, device=dev)
+        lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+        out_off = (torch.arange(B, dtype=torch.int64) * na).to(dev)
+        if len(_TOPO_CACHE) >= 16:
+            _TOPO_CACHE.pop(next(iter(_TOPO_CACHE)))
+        ent = _TOPO_CACHE[key] = (orders, slot, frame_of, lengths, out_off, info)
+    orders, slot, frame_of, lengths, out_off, _ = ent
     xyz = torch.zeros(B * na, 3, device=dev)
     N.check(N.lib().cb2_ic_to_xyz(N.dptr(ca), N.dptr(ic), B, L, N.dptr(frame_of), N.dptr(lengths), N.dptr(orders), N.dptr(slot),
                                   N.dptr(out_off), N.dptr(xyz), N.stream_ptr()), "ic_to_xyz")

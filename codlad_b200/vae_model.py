@@ -116,7 +116,7 @@ class VAE(nn.Module):
         """vae_model.py:830-839: quantise -> map_out -> IC decoder.  latent [B, L, 3] (already de-normalised),
         mask [B, L] bool, batch = reference batch dict (CG_nxyz, num_CGs, CG_nbr_list).  -> (None, ic_recon [sum L, 13, 3]).
         The decode-only plan (buffers) is kept per geometry (B, L); the frame data are re-uploaded on every call."""
-        num = batch["num_CGs"].to(torch.int64).cpu()
+        num = batch["num_CGs"].to(torch.int64)
         B, L = latent.shape[0], latent.shape[1]
         if num.numel() != B or int(num.max()) != L:
             raise ValueError("latent_decode: latent must be padded to the batch's max length, one row per frame")

@@ -93,7 +93,8 @@ CB2_API int cb2_plan_set_schedule(cb2_plan* p, const float* t_of_step, const flo
  * draws it with randn_like at :440).  use_graph != 0 captures the whole loop in one CUDA graph and replays it. */
 CB2_API int cb2_plan_sample(cb2_plan* p, float* x, const float* noise, int use_graph, void* stream);
 
-/* Decode-side geometry.  ca_full [F,L+2,3] device (untrimmed trace); HOST: csr_row_ptr [F*L+1] / csr_col [E]
+/* Decode-side geometry.  ca_full [F,L+2,3] device (untrimmed trace); HOST OR DEVICE (copied with
+ * cudaMemcpyDefault): csr_row_ptr [F*L+1] / csr_col [E]
  * = directed 21 A radius graph per frame (local column indices; make_directed, models/gcn_nn.py:54-64),
  * atom_orders [F,L,10,3] int8 and slot_atom [F,L*14] int32 (inverse of info's atom_idx[permute],
  * utils/protein_module.py:455-494), out_offset [NB] int64 = first output atom row of each member. */
