@@ -51,6 +51,27 @@ SIGNATURES = {
     "cb2_eval_bond_graphs": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, C.c_float, _P, _P, _P]),
 }
 
+# include/codlad_b200_train.h (the train_latent step)
+_F = C.c_float
+SIGNATURES.update({
+    "cb2t_gemm": (_I, [_P, _P, _P, _I, _I, _I, _LL, _LL, _LL, _I, _I, _I, _P]),
+    "cb2t_bias_gelu_fwd": (_I, [_P, _P, _LL, _I, _P, _P]),
+    "cb2t_gelu_bwd": (_I, [_P, _P, _LL, _P, _P]),
+    "cb2t_elementwise": (_I, [_I, _P, _P, _F, _LL, _P, _P]),
+    "cb2t_edge_combine_gelu_fwd": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _P]),
+    "cb2t_edge_gather_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "cb2t_masked_sum_fwd": (_I, [_P, _P, _I, _I, _F, _P, _P]),
+    "cb2t_masked_sum_bwd": (_I, [_P, _P, _I, _LL, _F, _P, _P]),
+    "cb2t_ln_mod_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _LL, _P, _F, _P, _P, _P, _P]),
+    "cb2t_ln_mod_bwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _I, _P]),
+    "cb2t_edge_raw_features": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "cb2t_row_gather_add": (_I, [_P, _P, _P, _LL, _P]),
+    "cb2t_index_sum": (_I, [_P, _P, _LL, _I, _I, _P, _I, _P]),
+    "cb2t_colsum": (_I, [_P, _LL, _I, _LL, _P, _I, _P]),
+    "cb2t_sumsq": (_I, [_P, _LL, _P, _P]),
+    "cb2t_adamw_ema": (_I, [_P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P, _F, _P]),
+})
+
 _lib = None
 
 

@@ -35,6 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "codlad_b200.h"))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "codlad_b200_train.h"))
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest(deps)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:

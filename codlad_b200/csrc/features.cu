@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) edge_features_kernel(
     const float* __restrict__ X, const int* __restrict__ nbr_idx, const float* __restrict__ nbr_dist, int L, int K,
     const float* __restrict__ pos_table, const float* __restrict__ wedge_t, const float* __restrict__ ln_w,
     const float* __restrict__ ln_b, const float* __restrict__ we_t, const float* __restrict__ we_b,
-    float* __restrict__ E_dbg, void* __restrict__ hE0) {
+    float* __restrict__ E_dbg, void* __restrict__ hE0, float* __restrict__ raw_out) {
     extern __shared__ __align__(16) float smem[];
     float* sRaw = smem;                       // [64][152]
     float* sE = sRaw + MAXK * RAW_LD;         // [64][128]
@@ -131,6 +131,12 @@ __global__ void __launch_bounds__(256) edge_features_kernel(
         }
     }
     __syncthreads();
+    if (raw_out != nullptr) {
+        // training step (train_ops.cu): the raw 144 RBF + 7 orientation features of every edge, [.., 152] (pad column zero); the
+        // trainable projections are applied -- and differentiated -- as separate GEMMs
+        for (int t = tid; t < K * RAW_LD; t += 256) raw_out[node * K * RAW_LD + t] = sRaw[t];
+        if (hE0 == nullptr) return;
+    }
 
     // ---- phase B: 151 -> 128 projection + positional table ----
     const int c = tid & 127, row0 = (tid >> 7) * 32;
@@ -195,11 +201,28 @@ int launch_edge_features(const DenoiserModel& m, const float* X, const int* leng
     dim3 grid(L, F);
     if (precision == PREC_F16) {
         CB2_CUDA(cudaFuncSetAttribute(edge_features_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        edge_features_kernel<true><<<grid, 256, smem, s>>>(X, idx, D, L, K, m.pos_table, m.wedge_t, m.ln_w, m.ln_b, m.we_t, m.we_b, E_dbg, hE0);
+        edge_features_kernel<true><<<grid, 256, smem, s>>>(X, idx, D, L, K, m.pos_table, m.wedge_t, m.ln_w, m.ln_b, m.we_t, m.we_b, E_dbg, hE0, nullptr);
     } else {
         CB2_CUDA(cudaFuncSetAttribute(edge_features_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        edge_features_kernel<false><<<grid, 256, smem, s>>>(X, idx, D, L, K, m.pos_table, m.wedge_t, m.ln_w, m.ln_b, m.we_t, m.we_b, E_dbg, hE0);
+        edge_features_kernel<false><<<grid, 256, smem, s>>>(X, idx, D, L, K, m.pos_table, m.wedge_t, m.ln_w, m.ln_b, m.we_t, m.we_b, E_dbg, hE0, nullptr);
     }
+    CB2_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_edge_raw_features(const float* X, const int* idx, const float* D, int F, int L, int K, float* raw_out, cudaStream_t s) {
+    if (K > MAXK) { set_error("edge_raw_features: K=%d > %d", K, MAXK); return (int)cudaErrorInvalidValue; }
+    static bool mu_ready = false;
+    if (!mu_ready) {
+        float mu[16];
+        const float step = (22.0f - 2.0f) / 15.0f;
+        for (int q = 0; q < 16; ++q) mu[q] = q < 8 ? 2.0f + step * q : 22.0f - step * (15 - q);
+        CB2_CUDA(cudaMemcpyToSymbol(c_rbf_mu, mu, sizeof(mu)));
+        mu_ready = true;
+    }
+    const size_t smem = (size_t)(MAXK * RAW_LD + MAXK * 128) * 4 + MAXK * 4 + 16 * 4;
+    CB2_CUDA(cudaFuncSetAttribute(edge_features_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    edge_features_kernel<false><<<dim3(L, F), 256, smem, s>>>(X, idx, D, L, K, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, raw_out);
     CB2_LAUNCH_CHECK();
     return 0;
 }

@@ -100,6 +100,7 @@ struct Plan {
 int launch_knn(const float* X, const int* lengths, int F, int L, int K, float* D, int* idx, cudaStream_t s);
 int launch_edge_features(const DenoiserModel& m, const float* X, const int* lengths, const int* idx, const float* D,
                          int F, int L, int K, float* E_dbg, void* hE0, int precision, cudaStream_t s);
+int launch_edge_raw_features(const float* X, const int* idx, const float* D, int F, int L, int K, float* raw_out, cudaStream_t s);
 int launch_timestep_mod(const DenoiserModel& m, const float* tvals, int n, float* scratch_silu_c, float* mod, __half* mod16, cudaStream_t s);
 int launch_p_sample(const float* x, const float* out6, const float* noise, const float* coef_rows, const int* step_of_row,
                     int rows_per_b, int n_rows, int C, float* x_next, cudaStream_t s);

@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "codlad_b200.h")).read()
-    return sorted(set(re.findall(r"CB2_API[^;(]*?\b(cb2_\w+)\s*\(", text)))
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("codlad_b200.h", "codlad_b200_train.h"))
+    return sorted(set(re.findall(r"CB2_API[^;(]*?\b(cb2t?_\w+)\s*\(", text)))
 
 
 def test_header_and_binding_agree():

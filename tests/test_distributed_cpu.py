@@ -125,3 +125,32 @@ def test_partition_and_grouping():
     lg = sb.local_groups([(0, 0), (0, 1), (2, 1), (2, 0), (1, 0)], [100, 50, 98])
     assert [g[0] for g in lg] == [[0, 2], [1]]
     assert lg[0][2] == [(0, 0), (2, 0), (0, 1), (2, 1)] and lg[0][1] == [0, 1, 0, 1]
+
+
+# ---- gradient all-reduce of the data-parallel train_latent step ---------------------------------------
+def _allreduce_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from codlad_b200.train import allreduce_flat
+    n = 2449974 + 37                                           # the reference's parameter count, not a multiple of the bucket count
+    g = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    allreduce_flat(g, n_buckets=4)
+    q.put((rank, float(g[1]), float(g[-1]), bool(torch.equal(g, torch.arange(n, dtype=torch.float32) * 1.5))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_averages_over_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, a, b, ok in res:
+        assert a == 1.5 and ok, (rank, a, b)
