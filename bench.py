@@ -289,6 +289,90 @@ def run_metrics(args):
                       "note": "gpu_ms_per_call is the public call (input checks, one small H2D copy of the offsets, two kernels)"}))
 
 
+# ------------------------------------------------------------------------------------------------ train_latent step (configs[4])
+def run_train(args):
+    """`--workload c5`: BASELINE configs[4] -- the train_latent step (denoiser forward + backward in train mode with the reference's
+    dropout 0.6, DDP gradient all-reduce over NCCL, clip + AdamW + EMA) on a synthetic PED-like batch of 128 proteins of ragged length
+    U[60, 400], global batch fixed (per-rank batch 128 / world, train_latent.py:54).  Not the bench line (that is the sampling path)."""
+    from codlad_b200 import distributed as D, synthetic, train, weights
+    from codlad_b200.diffusion import create_diffusion
+    rank, world, local = D.env_rank_world()
+    torch.cuda.set_device(local)
+    D.init_from_env("nccl", local)
+    dev = torch.device("cuda", local)
+    B_total, micro = 128, args.micro_batch
+    rnd = random.Random(5000)
+    lens = [rnd.randint(60, 400) for _ in range(B_total)]
+    per = B_total // world
+    mine = sorted(range(rank * per, (rank + 1) * per), key=lambda i: -lens[i])            # padded per micro-batch: group similar lengths
+    prots = {i: synthetic.make_protein(lens[i], 1, seed=5100 + i) for i in mine}
+    groups = [mine[k:k + micro] for k in range(0, len(mine), micro)]
+    batches = [synthetic.collate_many([prots[i] for i in g]) for g in groups]
+    gen = torch.Generator().manual_seed(77 + rank)
+    data = []
+    for g in groups:
+        Lm = max(lens[i] for i in g)
+        data.append((torch.randn(len(g), Lm, 3, generator=gen), torch.randint(0, 1000, (len(g),), generator=gen)))
+    tr = train.DenoiserTrainer(weights.init_denoiser_state(0), lr=1e-4)
+    diffusion = create_diffusion("")
+    dgen = torch.Generator(device=dev).manual_seed(5 + rank)
+
+    def one_step():
+        loss = 0.0
+        for k, (g, b, (x1, t)) in enumerate(zip(groups, batches, data)):
+            last = k == len(groups) - 1
+            _, l = tr.train_step(diffusion, x1, t, b, dropout_p=0.6, generator=dgen, zero=(k == 0), loss_weight=len(g) / per,
+                                 do_allreduce=last, do_step=last)
+            loss += l * len(g) / per
+        return loss
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        one_step()
+    D.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    losses = []
+    for a, b in ev:
+        a.record()
+        losses.append(one_step())
+        b.record()
+    D.barrier()
+    ms = D.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / args.steps, dev)
+    residues = sum(lens)
+    padded = D.gather_counts(sum(max(lens[i] for i in g) * len(g) for g in groups), dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import restate as R
+        threads = _cpu_setup(None)
+        torch.set_grad_enabled(True)
+        ids = mine[-2:]                                                                  # the two shortest proteins of the batch
+        Lm = max(lens[i] for i in ids)
+        X = torch.zeros(2, Lm, 3); z = torch.zeros(2, Lm, dtype=torch.int64)
+        for q, i in enumerate(ids):
+            X[q, :lens[i]] = prots[i].ca_full[0, 1:-1]; z[q, :lens[i]] = prots[i].restype_full[1:-1]
+        mask = torch.arange(Lm)[None] < torch.tensor([lens[i] for i in ids])[:, None]
+        leaves = {k: v.clone().requires_grad_(True) for k, v in weights.init_denoiser_state(0).items()}
+        t0 = time.perf_counter()
+        out = R.denoiser_forward(leaves, torch.randn(2, Lm, 3), torch.tensor([500, 10]), X, z, mask, 64)
+        (out ** 2).mean().backward()
+        cpu_s = time.perf_counter() - t0
+        torch.set_grad_enabled(False)
+        cpu = {"value": sum(lens[i] for i in ids) / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"torch.autograd through the CPU oracle's forward, 2 proteins ({[lens[i] for i in ids]} residues), one forward + backward, no optimiser"}
+    if rank == 0:
+        edges = sum(padded) * 64
+        flops = 3 * (884736 * edges + 2.16e6 * sum(padded))            # forward (canonical, SURVEY 8d) + two gradient GEMMs per linear layer
+        print(json.dumps({
+            "metric": "train_latent residues/sec (denoiser fwd+bwd, global batch 128, DDP all-reduce, AdamW+EMA)", "value": residues / (ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (SIMT GEMM)", "data": "synthetic",
+            "config": {"workload": "configs[4]: train_latent denoiser fwd+bwd, batch 128, PED-like ragged lengths U[60,400], dropout 0.6, DDP NCCL all-reduce",
+                       "per_rank_batch": per, "micro_batch": micro, "padded_residues_per_rank": padded, "residues": residues},
+            "loss": losses, "grad_norm": tr.grad_norm(), "achieved_tflops_fp32": flops / (ms * 1e-3) / 1e12,
+            "fp32_nominal_peak_tflops": FP32_NOMINAL_TFLOPS * world, "cpu_baseline": cpu,
+        }))
+    D.shutdown()
+
+
 # ------------------------------------------------------------------------------------------------ per-kernel rooflines
 def _time_stage(fn, flush, reps=10):
     """(cold us, warm us) of one launch: cold = L2 flushed before every launch, warm = back to back."""
@@ -468,18 +552,19 @@ def main():
     ap.add_argument("--impl", default="codlad_b200", choices=["codlad_b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CB2_PRECISION", "f16"), choices=["f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["metrics"],
-                    help="c2 = the bench line; c3 / c4 = per-GPU shards of the larger configs; metrics = the evaluation-step kernel")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["metrics", "c5"],
+                    help="c2 = the bench line; c3 / c4 = per-GPU shards of the larger configs; c5 = the train_latent step; metrics = the evaluation-step kernel")
+    ap.add_argument("--micro-batch", type=int, default=16, help="c5: proteins per forward/backward (gradients accumulate to the per-rank batch)")
     ap.add_argument("--scale", default="all", choices=["all", "c3", "c4", "none"], help="scale_checks jobs run through the sharded driver")
     ap.add_argument("--scale-passes", type=int, default=2)
     ap.add_argument("--lean", action="store_true", help="only value / e2e / roofline (no roofline_all, scale_checks, drop-in, CPU legs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "metrics":
+    if args.workload in ("metrics", "c5"):
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device: codlad_b200 has no CPU fallback")
-        return run_metrics(args)
+        return run_metrics(args) if args.workload == "metrics" else run_train(args)
     args.warmup = max(args.warmup, 3)
 
     from codlad_b200 import distributed as D

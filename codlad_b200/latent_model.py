@@ -78,7 +78,8 @@ class ProteinMPNN_diffusion_new(nn.Module):
 
     def train(self, mode: bool = True):
         if mode:
-            raise NotImplementedError("train_latent (SURVEY.md section 8, row f-1) is not built yet: this module is inference-only")
+            raise NotImplementedError("this module is the inference surface; the train_latent step (forward + backward + AdamW/EMA, SURVEY.md "
+                                      "section 8 row f-1) is codlad_b200.train.DenoiserTrainer, which takes this module's state_dict()")
         return super().train(False)
 
     # -- geometry ------------------------------------------------------------------------------------
