@@ -48,6 +48,7 @@ SIGNATURES = {
     "cb2_vq_lookup": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "cb2_p_sample": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "cb2_ic_to_xyz": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "cb2_superposed_rmsd": (_I, [_P, _P, _P, _I, _P, _P]),
     "cb2_eval_bond_graphs": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, C.c_float, _P, _P, _P]),
 }
 

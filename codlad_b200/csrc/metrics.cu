@@ -101,9 +101,72 @@ __global__ void __launch_bounds__(256) rmsd_sums_kernel(const float* __restrict_
     }
 }
 
+// Minimum RMSD under rigid superposition (what md.rmsd computes for the diversity score, test.py:37-96), per structure pair: the
+// 17 sums (centroids, inner products G_a / G_b, 3x3 cross-covariance) are accumulated in double over the atoms, then one thread takes
+// the largest eigenvalue of Horn's 4x4 key matrix with cyclic Jacobi rotations: rmsd^2 = (G_a + G_b - 2 lambda_max) / N.
+__global__ void __launch_bounds__(256) superposed_rmsd_kernel(const float* __restrict__ A, const float* __restrict__ B, const long long* __restrict__ offsets,
+                                                              double* __restrict__ out) {
+    const int s = blockIdx.x;
+    const long long base = offsets[s];
+    const int na = (int)(offsets[s + 1] - base);
+    double acc[17];
+    for (int k = 0; k < 17; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) {
+        double a[3], b[3];
+        for (int d = 0; d < 3; ++d) { a[d] = (double)A[(base + i) * 3 + d]; b[d] = (double)B[(base + i) * 3 + d]; }
+        for (int d = 0; d < 3; ++d) { acc[d] += a[d]; acc[3 + d] += b[d]; acc[6] += a[d] * a[d]; acc[7] += b[d] * b[d]; }
+        for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) acc[8 + 3 * p + q] += a[p] * b[q];
+    }
+    __shared__ double red[17][8];
+    for (int k = 0; k < 17; ++k) {
+        double v = acc[k];
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double t[17];
+    for (int k = 0; k < 17; ++k) { t[k] = 0.0; for (int w = 0; w < 8; ++w) t[k] += red[k][w]; }       // fixed order
+    if (na == 0) { out[s] = 0.0; return; }
+    const double n = (double)na;
+    double S[3][3];
+    for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) S[p][q] = t[8 + 3 * p + q] - t[p] * t[3 + q] / n;
+    const double Ga = t[6] - (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]) / n, Gb = t[7] - (t[3] * t[3] + t[4] * t[4] + t[5] * t[5]) / n;
+    double K[4][4] = {
+        {S[0][0] + S[1][1] + S[2][2], S[1][2] - S[2][1], S[2][0] - S[0][2], S[0][1] - S[1][0]},
+        {S[1][2] - S[2][1], S[0][0] - S[1][1] - S[2][2], S[0][1] + S[1][0], S[2][0] + S[0][2]},
+        {S[2][0] - S[0][2], S[0][1] + S[1][0], -S[0][0] + S[1][1] - S[2][2], S[1][2] + S[2][1]},
+        {S[0][1] - S[1][0], S[2][0] + S[0][2], S[1][2] + S[2][1], -S[0][0] - S[1][1] + S[2][2]}};
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 4; ++p) for (int q = p + 1; q < 4; ++q) off += K[p][q] * K[p][q];
+        if (off < 1e-30 * (Ga + Gb + 1e-300) * (Ga + Gb + 1e-300)) break;
+        for (int p = 0; p < 4; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                if (K[p][q] == 0.0) continue;
+                const double theta = (K[q][q] - K[p][p]) / (2.0 * K[p][q]);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+                for (int k = 0; k < 4; ++k) { const double kp = K[k][p], kq = K[k][q]; K[k][p] = c * kp - sn * kq; K[k][q] = sn * kp + c * kq; }
+                for (int k = 0; k < 4; ++k) { const double pk = K[p][k], qk = K[q][k]; K[p][k] = c * pk - sn * qk; K[q][k] = sn * pk + c * qk; }
+            }
+    }
+    const double lam = fmax(fmax(K[0][0], K[1][1]), fmax(K[2][2], K[3][3]));
+    out[s] = sqrt(fmax(0.0, (Ga + Gb - 2.0 * lam) / n));
+}
+
 }  // namespace
 
 }  // namespace cb2
+
+extern "C" int cb2_superposed_rmsd(const float* A, const float* B, const long long* offsets, int n_struct, double* out, void* stream) {
+    using namespace cb2;
+    if (!A || !B || !offsets || !out || n_struct < 0) { set_error("superposed_rmsd: bad argument"); return 1; }
+    if (n_struct == 0) return 0;
+    superposed_rmsd_kernel<<<n_struct, 256, 0, (cudaStream_t)stream>>>(A, B, offsets, out);
+    CB2_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int cb2_eval_bond_graphs(const float* xyz_ref, const float* xyz_gen, const int* atomic_num, const long long* offsets, int n_struct,
                                     int max_atoms, const float* cov_radius, int max_z, float scale, long long* counts, double* sums, void* stream) {

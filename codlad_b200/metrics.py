@@ -80,6 +80,41 @@ def valid_ratio_and_cut_off_result(xyz, xyz_recon, num_atoms, atomic_nums):
     return [float(v) for v in hv], [float(v) for v in av], [[float(v)] for v in hg], [[float(v)] for v in ag]
 
 
+def superposed_rmsd(xyz_a: torch.Tensor, xyz_b: torch.Tensor, num_atoms) -> torch.Tensor:
+    """Minimum RMSD under rigid superposition of structure pairs (md.rmsd as test.py:37-79 uses it).  xyz_* [sum Na, 3] (or
+    [n, Na, 3] with num_atoms = None) -> [n] float64 on the device (`cb2_superposed_rmsd`)."""
+    N.require_cuda()
+    dev = xyz_a.device if xyz_a.is_cuda else torch.device("cuda")
+    if num_atoms is None:
+        num_atoms = [xyz_a.shape[1]] * xyz_a.shape[0]
+    a = xyz_a.to(dev, torch.float32).reshape(-1, 3).contiguous()
+    b = xyz_b.to(dev, torch.float32).reshape(-1, 3).contiguous()
+    num = torch.as_tensor(num_atoms, dtype=torch.int64).cpu()
+    if a.shape != b.shape or int(num.sum()) != a.shape[0]:
+        raise ValueError("superposed_rmsd: the two sets do not describe the same atoms")
+    offsets = torch.zeros(num.numel() + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(num, 0)
+    out = torch.empty(num.numel(), dtype=torch.float64, device=dev)
+    N.check(N.lib().cb2_superposed_rmsd(N.dptr(a), N.dptr(b), N.dptr(offsets.to(dev)), int(num.numel()), N.dptr(out), N.stream_ptr()), "superposed_rmsd")
+    return out
+
+
+def compute_div(gen_structures, ref_structure):
+    """test.py:37-96 (compute_rmsd_ref, compute_rmsd_gen, compute_div): DIV = 1 - mean rmsd(gen, mean gen) / mean rmsd(gen, ref) over the
+    G generated ensembles `gen_structures` (list of [P, Na, 3]) of P structures and their reference [P, Na, 3]; every RMSD is the
+    superposed one.  Returns (div, rmsd_ref, rmsd_gen) as Python floats."""
+    gen = torch.stack([torch.as_tensor(g, dtype=torch.float32) for g in gen_structures], 0)          # [G, P, Na, 3]
+    ref = torch.as_tensor(ref_structure, dtype=torch.float32)
+    G, P, Na, _ = gen.shape
+    dev = gen.device if gen.is_cuda else torch.device("cuda")
+    gen, ref = gen.to(dev), ref.to(dev)
+    mean_gen = gen.mean(0)                                                                            # np.mean(gen_structures, axis=0)
+    flat = gen.reshape(G * P, Na, 3)
+    rmsd_ref = superposed_rmsd(flat, ref[None].expand(G, -1, -1, -1).reshape(G * P, Na, 3), None).mean()
+    rmsd_gen = superposed_rmsd(flat, mean_gen[None].expand(G, -1, -1, -1).reshape(G * P, Na, 3), None).mean()
+    return float(1.0 - rmsd_gen / rmsd_ref), float(rmsd_ref), float(rmsd_gen)
+
+
 # -- elementwise evaluation losses (test.py:97-166); torch ops on the inputs' device ------------------------------------------
 def _pair_dist(xyz, pairs):
     return ((xyz[pairs[:, 0]] - xyz[pairs[:, 1]]).pow(2).sum(-1) + EPS).sqrt()

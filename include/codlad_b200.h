@@ -158,6 +158,12 @@ CB2_API int cb2_ic_to_xyz(const float* ca_full, const float* ic_recon, int NB, i
 CB2_API int cb2_eval_bond_graphs(const float* xyz_ref, const float* xyz_gen, const int* atomic_num, const long long* offsets, int n_struct,
                          int max_atoms, const float* cov_radius, int max_z, float scale, long long* counts, double* sums, void* stream);
 
+/* Replaces: md.rmsd(Trajectory(a), Trajectory(b)) as the diversity score uses it (compute_rmsd_ref / compute_rmsd_gen / compute_div,
+ * test.py:37-96): the minimum RMSD under rigid superposition of structure pairs.  A, B [sum Na, 3] DEVICE (pair s = atoms
+ * offsets[s] .. offsets[s+1] of both), out [n_struct] double.  Sums in double, largest eigenvalue of Horn's quaternion matrix.
+ * mdtraj is absent from the build container: parity is against a float64 Kabsch (SVD) restatement, i.e. unpinned against mdtraj itself. */
+CB2_API int cb2_superposed_rmsd(const float* A, const float* B, const long long* offsets, int n_struct, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -539,3 +539,26 @@ def sample_quality_stats(xyz_ref, xyz_gen, z, num_atoms, scale=1.3):
         sums.append([float(d2.sum()), float(na), float(d2[heavy].sum()), float(heavy.sum())])
         o += na
     return torch.tensor(counts, dtype=torch.int64), torch.tensor(sums, dtype=torch.float64)
+
+
+def superposed_rmsd(a, b):
+    """md.rmsd(Trajectory(a), Trajectory(b)) as test.py:37-79 uses it: minimum RMSD of two [Na, 3] structures under rigid
+    superposition.  mdtraj (absent here: parity unpinned against it) computes it with Theobald's QCP in float32; this is the
+    float64 Kabsch form of the same quantity: rmsd^2 = (|a_c|^2 + |b_c|^2 - 2 sum_i sigma_i d_i) / N with d = (1, 1, sign det)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    ac, bc = a - a.mean(0), b - b.mean(0)
+    u, sig, vt = np.linalg.svd(ac.T @ bc)
+    d = np.ones(3)
+    d[2] = np.sign(np.linalg.det(u @ vt))
+    return float(np.sqrt(max(0.0, ((ac ** 2).sum() + (bc ** 2).sum() - 2.0 * (sig * d).sum()) / a.shape[0])))
+
+
+def compute_div(gen_structures, ref_structure):
+    """compute_div (test.py:82-96) on numpy arrays: 1 - mean rmsd(gen, mean gen) / mean rmsd(gen, ref)."""
+    gen = np.asarray(gen_structures, dtype=np.float64)
+    ref = np.asarray(ref_structure, dtype=np.float64)
+    mean_gen = gen.mean(0)
+    r_ref = np.mean([superposed_rmsd(gen[i][p], ref[p]) for i in range(gen.shape[0]) for p in range(gen.shape[1])])
+    r_gen = np.mean([superposed_rmsd(gen[i][p], mean_gen[p]) for i in range(gen.shape[0]) for p in range(gen.shape[1])])
+    return 1.0 - r_gen / r_ref, r_ref, r_gen

@@ -682,3 +682,27 @@ def test_bond_graph_metrics_on_backmapped_ensemble(eng, R):
     assert torch.equal(counts.cpu(), c_ref)
     assert torch.allclose(sums.cpu(), s_ref, rtol=1e-12, atol=0)
     assert int(counts[0, 0]) == 0 and int(counts[1, 0]) == 0    # members 0 are scored against themselves
+
+
+def test_superposed_rmsd_and_diversity_vs_oracle(R):
+    """cb2_superposed_rmsd / metrics.compute_div (test.py:37-96) against the float64 Kabsch restatement: rotated + translated copies give
+    0, noisy copies agree to 1e-6 relative, reflections are not allowed (a mirrored structure keeps a finite RMSD), ragged sizes."""
+    from codlad_b200 import metrics
+    g = torch.Generator().manual_seed(9)
+    sizes = [517, 60, 2479, 3]
+    A = [torch.randn(n, 3, generator=g) * 8 for n in sizes]
+    q = torch.randn(4, generator=g); q = q / q.norm()
+    w, x, y, z = q.tolist()
+    Rm = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    B = [a @ Rm.T + torch.tensor([3.0, -7.0, 11.0]) + (0.0 if k == 0 else 0.3) * torch.randn(a.shape, generator=g) for k, a in enumerate(A)]
+    B[1] = A[1] * torch.tensor([1.0, 1.0, -1.0])                      # mirror image
+    got = metrics.superposed_rmsd(torch.cat(A), torch.cat(B), sizes).cpu()
+    want = torch.tensor([R.superposed_rmsd(a.numpy(), b.numpy()) for a, b in zip(A, B)], dtype=torch.float64)
+    assert float(got[0]) < 1e-5 and float(want[1]) > 1.0
+    assert torch.allclose(got[1:], want[1:], rtol=1e-6, atol=1e-9), (got, want)
+    gen = [torch.randn(3, 200, 3, generator=g) * 5 for _ in range(4)]
+    ref = torch.randn(3, 200, 3, generator=g) * 5
+    div, r_ref, r_gen = metrics.compute_div(gen, ref)
+    d0, a0, b0 = R.compute_div([v.numpy() for v in gen], ref.numpy())
+    assert abs(div - d0) < 1e-6 and abs(r_ref - a0) < 1e-5 * a0 and abs(r_gen - b0) < 1e-5 * b0

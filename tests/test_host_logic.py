@@ -196,3 +196,17 @@ def test_training_losses_values_match_reference_golden():
         assert torch.allclose(terms[k], torch.from_numpy(g[k]), rtol=2e-5, atol=1e-6), k
     nomask = diff.training_losses(model, x_start, t, {}, noise=noise)
     assert torch.allclose(nomask["loss"], torch.from_numpy(g["loss_nomask"]), rtol=2e-5, atol=1e-6)
+
+
+def test_oracle_superposed_rmsd_known_answers():
+    """The float64 Kabsch restatement of md.rmsd (oracle, test infrastructure): invariance under rotation / translation, no reflection,
+    and a closed-form case (two points at distance 2 vs distance 4 -> rmsd 1 after centring)."""
+    import numpy as np
+    from oracle import restate as R
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(50, 3))
+    th = 0.7
+    rot = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    assert R.superposed_rmsd(a, a @ rot.T + 5.0) < 1e-12
+    assert R.superposed_rmsd(a, a * np.array([1, 1, -1])) > 0.1
+    assert abs(R.superposed_rmsd(np.array([[-1.0, 0, 0], [1.0, 0, 0]]), np.array([[0, -2.0, 0], [0, 2.0, 0]])) - 1.0) < 1e-12
