@@ -101,18 +101,29 @@ class ProteinMPNN_diffusion_new(nn.Module):
         F, L = len(num_l), max(num_l)
         if n_members % F != 0:
             raise ValueError(f"batch of {n_members} rows over {F} frames")
-        geo = (F, int(n_members), L)
         cg_host = cg.detach().to("cpu", torch.float32)
+        # frames of the batch that are byte-identical (an ensemble written as repeated frames, test.py's doubled batch) share one
+        # k-NN graph / feature set: the plan holds the DISTINCT frames and maps every batch row to one of them
+        X, z = batching.pad_frames(cg_host, torch.tensor(num_l), L)
+        first, uniq, of_frame = {}, [], []
+        for f in range(F):
+            key = (num_l[f], X[f].numpy().tobytes(), z[f].numpy().tobytes())
+            if key not in first:
+                first[key] = len(uniq)
+                uniq.append(f)
+            of_frame.append(first[key])
+        Fu = len(uniq)
+        geo = (Fu, int(n_members), L)
         ent = self._plans.get(geo)
         if ent is None:
             if len(self._plans) >= 4:                  # a sampling run alternates between very few geometries
                 self._plans.pop(next(iter(self._plans)))["plan"].close()
-            ent = {"plan": Plan(self.engine(), F, int(n_members), L, self.precision), "cg": None, "num": None, "n_members": int(n_members),
+            ent = {"plan": Plan(self.engine(), Fu, int(n_members), L, self.precision), "cg": None, "num": None, "n_members": int(n_members),
                    "bufs": None, "schedule": None}
             self._plans[geo] = ent
         if ent["num"] != num_l or ent["cg"] is None or not torch.equal(ent["cg"], cg_host):
-            X, z = batching.pad_frames(cg_host, torch.tensor(num_l), L)
-            ent["plan"].set_frames(X, torch.tensor(num_l, dtype=torch.int32), z, torch.arange(F, dtype=torch.int32).repeat(n_members // F))
+            frame_of = torch.tensor(of_frame, dtype=torch.int32).repeat(n_members // F)
+            ent["plan"].set_frames(X[uniq].contiguous(), torch.tensor([num_l[f] for f in uniq], dtype=torch.int32), z[uniq].contiguous(), frame_of)
             ent["cg"], ent["num"] = cg_host.clone(), num_l
         ent["cg_ref"], ent["num_ref"], ent["version"] = cg, num, (cg._version, num._version)
         self._last = ent

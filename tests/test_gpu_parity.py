@@ -706,3 +706,25 @@ def test_superposed_rmsd_and_diversity_vs_oracle(R):
     div, r_ref, r_gen = metrics.compute_div(gen, ref)
     d0, a0, b0 = R.compute_div([v.numpy() for v in gen], ref.numpy())
     assert abs(div - d0) < 1e-6 and abs(r_ref - a0) < 1e-5 * a0 and abs(r_gen - b0) < 1e-5 * b0
+
+
+def test_repeated_frames_in_a_batch_share_their_precompute():
+    """An ensemble written as repeated frames in the reference batch schema (and test.py's doubled batch) is served by a plan that holds the
+    DISTINCT frames only; results equal those of one-frame batches row by row."""
+    from codlad_b200.latent_model import MPNN_models
+    model = MPNN_models["mpnn_diffusion"](precision="fp32")
+    model.load_state_dict(weights.init_denoiser_state(0))
+    L = 44
+    p2 = synthetic.make_protein(L, 2, seed=808)                      # two conformations of one protein
+    batch = synthetic.collate(p2, frames=[0, 1, 0, 0, 1])
+    x = synthetic.latent_noise((5, L, 3), 4).cuda()
+    t = torch.tensor([10.0, 500.0, 999.0, 10.0, 250.0]).cuda()
+    mask = torch.ones(5, L, dtype=torch.bool).cuda()
+    out = model(x, t, None, mask=mask, batch=batch).cpu()
+    plan = model.plan_for(batch, 5)
+    assert plan.F == 2 and plan.NB == 5
+    for b, f in enumerate([0, 1, 0, 0, 1]):
+        solo = MPNN_models["mpnn_diffusion"](precision="fp32")
+        solo.load_state_dict(weights.init_denoiser_state(0))
+        one = solo(x[b:b + 1], t[b:b + 1], None, mask=mask[:1], batch=synthetic.collate(p2, frames=[f])).cpu()
+        assert torch.equal(out[b:b + 1], one), b
