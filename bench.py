@@ -313,7 +313,7 @@ def run_train(args):
     for g in groups:
         Lm = max(lens[i] for i in g)
         data.append((torch.randn(len(g), Lm, 3, generator=gen), torch.randint(0, 1000, (len(g),), generator=gen)))
-    tr = train.DenoiserTrainer(weights.init_denoiser_state(0), lr=1e-4)
+    tr = train.DenoiserTrainer(weights.init_denoiser_state(0), lr=1e-4, gemm=args.train_gemm)
     diffusion = create_diffusion("")
     dgen = torch.Generator(device=dev).manual_seed(5 + rank)
 
@@ -364,10 +364,10 @@ def run_train(args):
         print(json.dumps({
             "metric": "train_latent residues/sec (denoiser fwd+bwd, global batch 128, DDP all-reduce, AdamW+EMA)", "value": residues / (ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (SIMT GEMM)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "tf32 (tcgen05 kind::tf32, fp32 accumulate and storage)" if args.train_gemm == "tf32" else "f32 (SIMT GEMM)", "data": "synthetic",
             "config": {"workload": "configs[4]: train_latent denoiser fwd+bwd, batch 128, PED-like ragged lengths U[60,400], dropout 0.6, DDP NCCL all-reduce",
                        "per_rank_batch": per, "micro_batch": micro, "padded_residues_per_rank": padded, "residues": residues},
-            "loss": losses, "grad_norm": tr.grad_norm(), "achieved_tflops_fp32": flops / (ms * 1e-3) / 1e12,
+            "loss": losses, "grad_norm": tr.grad_norm(), "achieved_tflops": flops / (ms * 1e-3) / 1e12,
             "fp32_nominal_peak_tflops": FP32_NOMINAL_TFLOPS * world, "cpu_baseline": cpu,
         }))
     D.shutdown()
@@ -554,7 +554,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["metrics", "c5"],
                     help="c2 = the bench line; c3 / c4 = per-GPU shards of the larger configs; c5 = the train_latent step; metrics = the evaluation-step kernel")
-    ap.add_argument("--micro-batch", type=int, default=16, help="c5: proteins per forward/backward (gradients accumulate to the per-rank batch)")
+    ap.add_argument("--train-gemm", default="tf32", choices=["tf32", "fp32"], help="c5: TF32 tensor-core GEMMs (the reference's arithmetic) or fp32 SIMT")
+    ap.add_argument("--micro-batch", type=int, default=64, help="c5: proteins per forward/backward (gradients accumulate to the per-rank batch)")
     ap.add_argument("--scale", default="all", choices=["all", "c3", "c4", "none"], help="scale_checks jobs run through the sharded driver")
     ap.add_argument("--scale-passes", type=int, default=2)
     ap.add_argument("--lean", action="store_true", help="only value / e2e / roofline (no roofline_all, scale_checks, drop-in, CPU legs)")

@@ -13,6 +13,8 @@
 namespace cb2 {
 namespace train {
 
+int g_gemm_mode = 0;
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8, THREADS = 256;
@@ -153,6 +155,8 @@ int launch(const GemmArgs& g, dim3 grid, bool vec, cudaStream_t s) {
 int gemm(const float* A, const float* B, float* C, int M, int N, int K, long long lda, long long ldb, long long ldc, int a_kc, int b_kc,
          int accumulate, cudaStream_t s) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
+    if (g_gemm_mode == 1 && tc_shape_ok(A, B, C, M, N, K, lda, ldb, ldc, a_kc, b_kc))
+        return a_kc ? gemm_tc_nt(A, B, C, M, N, K, lda, ldb, ldc, accumulate, s) : gemm_tc_tn(A, B, C, M, N, K, lda, ldb, ldc, accumulate, s);
     GemmArgs g{A, B, C, M, N, K, lda, ldb, ldc, K, accumulate, nullptr};
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
     const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);

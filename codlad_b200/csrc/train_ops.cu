@@ -256,35 +256,57 @@ __global__ void ln_mod_bwd_reduce_kernel(const float* __restrict__ part, int chu
     *dst = accumulate ? *dst + s : s;
 }
 
-// out[c, :] (+)= sum of the rows whose index is c (embedding gradients: W_s, the positional one-hot); one CTA per class
-__global__ void __launch_bounds__(256) index_sum_kernel(const float* __restrict__ X, const int* __restrict__ idx, long long n, int cols, float* __restrict__ out,
-                                                        int accumulate) {
-    __shared__ float sRed[256];
-    const int c = blockIdx.x;
-    const int lanes = cols;                               // cols <= 128: thread (row slot, column)
-    const int slots = 256 / lanes;
-    const int col = threadIdx.x % lanes, slot = threadIdx.x / lanes;
+// out[c, :] (+)= sum of the rows whose index is c (embedding gradients: W_s, the positional one-hot).  Two passes, both in a fixed
+// order: a CTA walks a contiguous chunk of rows, thread = column, per-class sums in shared memory (a thread owns its column: no
+// conflicts, no atomics); then the chunks are added up.
+constexpr int IDX_MAX_CLASSES = 72;
+__global__ void __launch_bounds__(128) index_sum_part_kernel(const float* __restrict__ X, const int* __restrict__ idx, long long n, int cols, int classes,
+                                                             int rows_per_cta, float* __restrict__ part) {
+    __shared__ float acc[IDX_MAX_CLASSES][128];
+    const int col = threadIdx.x;
+    for (int c = 0; c < classes; ++c) acc[c][col] = 0.f;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+    if (col < cols)
+        for (long long r = r0; r < r1; ++r) acc[__ldg(idx + r)][col] += X[r * cols + col];
+    if (col < cols)
+        for (int c = 0; c < classes; ++c) part[((long long)blockIdx.x * classes + c) * cols + col] = acc[c][col];
+}
+__global__ void index_sum_reduce_kernel(const float* __restrict__ part, int n_part, int total, float* __restrict__ out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
     float s = 0.f;
-    if (slot < slots)
-        for (long long r = slot; r < n; r += slots)
-            if (__ldg(idx + r) == c) s += X[r * cols + col];
-    sRed[threadIdx.x] = (slot < slots) ? s : 0.f;
-    __syncthreads();
-    if (threadIdx.x < lanes) {
-        float t = 0.f;
-        for (int q = 0; q < slots; ++q) t += sRed[q * lanes + threadIdx.x];
-        float* dst = out + (long long)c * cols + threadIdx.x;
-        *dst = accumulate ? *dst + t : t;
-    }
+    for (int q = 0; q < n_part; ++q) s += part[(long long)q * total + i];
+    out[i] = accumulate ? out[i] + s : s;
 }
 
-// column sums of X [rows, cols] (bias gradients), two passes, fixed order
+// column sums of X [rows, cols] (bias gradients), two passes, fixed order.  Fast path (cols % 4 == 0, cols <= 1024): thread = one float4
+// column group of one row lane, 256 threads cover 256 / (cols / 4) rows per iteration.
 __global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restrict__ X, long long rows, int cols, long long ld, int rows_per_cta, float* __restrict__ part) {
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
     for (int c = threadIdx.x; c < cols; c += 256) {
         float s = 0.f;
         for (long long r = r0; r < r1; ++r) s += X[r * ld + c];
         part[(long long)blockIdx.x * cols + c] = s;
+    }
+}
+__global__ void __launch_bounds__(256) colsum_part_vec_kernel(const float* __restrict__ X, long long rows, int cols, long long ld, int rows_per_cta, float* __restrict__ part) {
+    __shared__ float4 red[256];
+    const int groups = cols >> 2;                         // float4 column groups (<= 256)
+    const int lanes = 256 / groups;                       // row lanes
+    const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes)
+        for (long long r = r0 + lane; r < r1; r += lanes) {
+            const float4 v = *reinterpret_cast<const float4*>(X + r * ld + cg * 4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { const float4 v = red[l * groups + threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }      // fixed order
+        *reinterpret_cast<float4*>(part + (long long)blockIdx.x * cols + threadIdx.x * 4) = t;
     }
 }
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int n_part, int cols, float* __restrict__ out, int accumulate) {
@@ -363,6 +385,12 @@ int cb2t_gemm(const float* A, const float* B, float* C, int M, int N, int K, lon
               int accumulate, void* stream) {
     if (!A || !B || !C) { set_error("cb2t_gemm: null argument"); return 1; }
     return gemm(A, B, C, M, N, K, lda, ldb, ldc, a_kc, b_kc, accumulate, (cudaStream_t)stream);
+}
+
+int cb2t_set_gemm_mode(int mode) {
+    if (mode != 0 && mode != 1) { set_error("cb2t_set_gemm_mode: 0 (fp32 SIMT) or 1 (TF32 tensor cores)"); return 1; }
+    g_gemm_mode = mode;
+    return 0;
 }
 
 int cb2t_bias_gelu_fwd(float* Z, const float* bias, long long rows, int cols, float* Y, void* stream) {
@@ -460,19 +488,31 @@ int cb2t_row_gather_add(float* Z, const float* T, const int* idx, long long rows
 }
 
 int cb2t_index_sum(const float* X, const int* idx, long long n, int cols, int classes, float* out, int accumulate, void* stream) {
-    if (!X || !idx || !out || cols <= 0 || cols > 128 || 256 % cols != 0) { set_error("cb2t_index_sum: cols must divide 256 and be <= 128"); return 1; }
-    index_sum_kernel<<<classes, 256, 0, (cudaStream_t)stream>>>(X, idx, n, cols, out, accumulate);
+    if (!X || !idx || !out || cols <= 0 || cols > 128 || classes <= 0 || classes > IDX_MAX_CLASSES) {
+        set_error("cb2t_index_sum: cols <= 128 and classes <= %d", IDX_MAX_CLASSES);
+        return 1;
+    }
+    const int n_part = (int)(n < 592 * 64 ? (n + 63) / 64 : 592);
+    const int rows_per_cta = (int)((n + n_part - 1) / n_part);
+    float* part = nullptr;
+    if (int e = workspace((size_t)n_part * classes * cols * sizeof(float), &part)) return e;
+    index_sum_part_kernel<<<n_part, 128, 0, (cudaStream_t)stream>>>(X, idx, n, cols, classes, rows_per_cta, part);
+    CB2_LAUNCH_CHECK();
+    const int total = classes * cols;
+    index_sum_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, n_part, total, out, accumulate);
     CB2_LAUNCH_CHECK();
     return 0;
 }
 
 int cb2t_colsum(const float* X, long long rows, int cols, long long ld, float* out, int accumulate, void* stream) {
     if (!X || !out) { set_error("cb2t_colsum: null argument"); return 1; }
-    const int n_part = (int)(rows < 296 * 64 ? (rows + 63) / 64 : 296);
+    const int n_part = (int)(rows < 1184 * 32 ? (rows + 31) / 32 : 1184);
     const int rows_per_cta = (int)((rows + n_part - 1) / n_part);
     float* part = nullptr;
     if (int e = workspace((size_t)n_part * cols * sizeof(float), &part)) return e;
-    colsum_part_kernel<<<n_part, 256, 0, (cudaStream_t)stream>>>(X, rows, cols, ld, rows_per_cta, part);
+    const bool vec = cols % 4 == 0 && cols <= 1024 && 256 % (cols / 4) == 0 && ld % 4 == 0 && reinterpret_cast<uintptr_t>(X) % 16 == 0;
+    if (vec) colsum_part_vec_kernel<<<n_part, 256, 0, (cudaStream_t)stream>>>(X, rows, cols, ld, rows_per_cta, part);
+    else colsum_part_kernel<<<n_part, 256, 0, (cudaStream_t)stream>>>(X, rows, cols, ld, rows_per_cta, part);
     CB2_LAUNCH_CHECK();
     colsum_reduce_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, n_part, cols, out, accumulate);
     CB2_LAUNCH_CHECK();

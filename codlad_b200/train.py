@@ -42,6 +42,7 @@ class _Ops:
 
     def __init__(self):
         self.lib = N.lib()
+        self.transposed = {}           # data_ptr of a weight view -> its transposed copy (TF32 mode only)
 
     def gemm(self, A, B, Cm, M, Nn, K, lda, ldb, ldc, a_kc, b_kc, acc=False):
         N.check(self.lib.cb2t_gemm(A, B, Cm, int(M), int(Nn), int(K), int(lda), int(ldb), int(ldc), int(a_kc), int(b_kc), int(acc), N.stream_ptr()),
@@ -58,7 +59,11 @@ class _Ops:
     def linear_dx(self, dy, W, c0, kin, out=None, acc=False):
         M, nout, ldw = dy.shape[0], W.shape[0], W.shape[1]
         dx = out if out is not None else torch.empty(M, kin, device=dy.device, dtype=torch.float32)
-        self.gemm(dy.data_ptr(), W.data_ptr() + 4 * c0, dx.data_ptr(), M, kin, nout, dy.stride(0), ldw, dx.stride(0), 1, 0, acc)
+        Wt = self.transposed.get(W.data_ptr())
+        if Wt is not None:             # TF32 mode: both operands K-contiguous (B = rows c0.. of W^T [in_total, out])
+            self.gemm(dy.data_ptr(), Wt.data_ptr() + 4 * c0 * nout, dx.data_ptr(), M, kin, nout, dy.stride(0), nout, dx.stride(0), 1, 1, acc)
+        else:
+            self.gemm(dy.data_ptr(), W.data_ptr() + 4 * c0, dx.data_ptr(), M, kin, nout, dy.stride(0), ldw, dx.stride(0), 1, 0, acc)
         return dx
 
     # dW[:, c0:c0+in] += dy[M, out]^T @ x[M, in]
@@ -175,8 +180,13 @@ class DenoiserTrainer:
     with the reference's state_dict names and shapes."""
 
     def __init__(self, state_dict: dict, k_neighbors: int = 64, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, ema_decay: float = 0.9999, grad_clip: float = 1.0, device=None):
+                 weight_decay: float = 0.0, ema_decay: float = 0.9999, grad_clip: float = 1.0, device=None, gemm: str = "fp32"):
+        """gemm = "fp32": every GEMM on the fp32 SIMT path (gradient parity against fp32 autograd); "tf32": tensor cores (tcgen05.mma
+        kind::tf32, fp32 accumulation) for the large GEMMs -- the arithmetic the reference trains with (train_latent.py:24-25)."""
         N.require_cuda()
+        if gemm not in ("fp32", "tf32"):
+            raise ValueError("gemm must be 'fp32' or 'tf32'")
+        self.gemm_mode = gemm
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.ops = _Ops()
         self.k_neighbors = int(k_neighbors)
@@ -198,10 +208,27 @@ class DenoiserTrainer:
         for k in shapes:
             self.params[k].copy_(sd[k].to(self.device, torch.float32))
         self.flat_ema.copy_(self.flat_p)
+        self._refresh_transposed()
         self.step_count = 0
         self.freqs = sinusoid_freqs().to(self.device)
         self.sumsq = torch.zeros(1, device=self.device)
         self.ctx = None
+
+    def _refresh_transposed(self):
+        """TF32 mode: W^T copies of the 2-D weights, so that the data gradients are K-contiguous on both operands (layout change only)."""
+        if self.gemm_mode != "tf32":
+            self.ops.transposed.clear()
+            return
+        for k, w in self.params.items():
+            if w.dim() == 2 and w.shape[0] % 4 == 0 and w.shape[1] >= 32:
+                cur = self.ops.transposed.get(w.data_ptr())
+                if cur is None:
+                    self.ops.transposed[w.data_ptr()] = w.t().contiguous()
+                else:
+                    cur.copy_(w.t())
+
+    def _set_mode(self):
+        N.check(self.ops.lib.cb2t_set_gemm_mode(1 if self.gemm_mode == "tf32" else 0), "set_gemm_mode")
 
     def state_dict(self, ema: bool = False):
         src = self.ema if ema else self.params
@@ -296,6 +323,7 @@ class DenoiserTrainer:
     def forward(self, x, t, geom: Geometry, dropout_p: float = 0.0, generator=None):
         """x [B, L, 3] fp32, t [B] (original 0..999 scale) -> model output [B, L, 6]; the activations the backward needs are kept."""
         o, P, g = self.ops, self.params, geom
+        self._set_mode()
         ctx = {"geom": g}
         x2 = x.to(self.device, torch.float32).reshape(g.Nn, 3).contiguous()
         # timestep embedder (latent_model.py:37-75) and the SiLU in front of every adaLN projection
@@ -453,6 +481,7 @@ class DenoiserTrainer:
     def backward(self, dout):
         """dout [B, L, 6] = d loss / d model output -> self.grads (+=; call zero_grad() first)."""
         o, P, G, ctx = self.ops, self.params, self.grads, self.ctx
+        self._set_mode()
         g = ctx["geom"]
         d_c_silu = torch.zeros(g.B, H, device=self.device)
         dout2 = dout.to(self.device, torch.float32).reshape(g.Nn, 6).contiguous()
@@ -516,6 +545,7 @@ class DenoiserTrainer:
         N.check(lib.cb2t_adamw_ema(_p(self.flat_p), _p(self.flat_g), _p(self.flat_m), _p(self.flat_v), _p(self.flat_ema), self.numel,
                                    hp["lr"] * lr_scale, hp["b1"], hp["b2"], hp["eps"], hp["wd"], self.step_count, hp["ema"],
                                    _p(self.sumsq), hp["clip"] if hp["clip"] else 0.0, N.stream_ptr()), "adamw_ema")
+        self._refresh_transposed()
 
     def grad_norm(self) -> float:
         return float(self.sumsq.sqrt().item())

@@ -25,6 +25,12 @@ extern "C" {
 CB2_API int cb2t_gemm(const float* A, const float* B, float* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
                       int a_kc, int b_kc, int accumulate, void* stream);
 
+/* Arithmetic of cb2t_gemm: 0 = fp32 SIMT everywhere (the gradient-parity mode), 1 = TF32 tensor cores (tcgen05.mma kind::tf32, fp32
+ * accumulation) wherever the shape allows -- what the reference itself trains with (train_latent.py:24-25, allow_tf32 = True): forward
+ * and data gradients when both operands are K-contiguous (pass W^T for dgrad), weight gradients when both are MN-contiguous and the
+ * output is made of full 128 x 128 blocks; everything else stays on the SIMT path. */
+CB2_API int cb2t_set_gemm_mode(int mode);
+
 /* Replaces: `+ bias` and torch.nn.GELU() (exact erf form; protein_mpnn_utils.py:227,243,325).  Z [rows, cols] <- Z + bias (kept as the
  * pre-activation), Y <- GELU(Z) when Y != NULL.  bias may be NULL. */
 CB2_API int cb2t_bias_gelu_fwd(float* Z, const float* bias, long long rows, int cols, float* Y, void* stream);
@@ -70,7 +76,7 @@ CB2_API int cb2t_edge_raw_features(const float* X, const int* idx, const float* 
 CB2_API int cb2t_row_gather_add(float* Z, const float* T, const int* idx, long long rows, void* stream);
 
 /* Replaces: the autograd of an embedding lookup (W_s, latent_model.py:225; the one-hot of PositionalEncodings, protein_mpnn_utils.py:340-343):
- * out[c, :] (+)= sum of the rows of X [n, cols] with idx == c.  cols must divide 256. */
+ * out[c, :] (+)= sum of the rows of X [n, cols] with idx == c.  cols <= 128, classes <= 72. */
 CB2_API int cb2t_index_sum(const float* X, const int* idx, long long n, int cols, int classes, float* out, int accumulate, void* stream);
 /* Bias gradients: out[c] (+)= sum_r X[r * ld + c]. */
 CB2_API int cb2t_colsum(const float* X, long long rows, int cols, long long ld, float* out, int accumulate, void* stream);

@@ -728,3 +728,28 @@ def test_repeated_frames_in_a_batch_share_their_precompute():
         solo.load_state_dict(weights.init_denoiser_state(0))
         one = solo(x[b:b + 1], t[b:b + 1], None, mask=mask[:1], batch=synthetic.collate(p2, frames=[f])).cpu()
         assert torch.equal(out[b:b + 1], one), b
+
+
+def test_sharded_backmapper_maps_every_unit_to_its_frame():
+    """sampler.ShardedBackmapper on one rank (the multi-rank exchange is covered on CPU with gloo): ragged proteins are grouped into padded
+    plans, every (frame, member) unit comes back with its frame's atom count, and the C-alpha atoms of each structure ARE the input trace
+    of that frame (slot 3 of ic_to_xyz copies it, utils_ic.py:247-266) -- so a unit can not have been decoded on another frame's geometry."""
+    from codlad_b200 import sampler
+    lengths = [90, 41, 88, 64, 43]
+    prots = [synthetic.make_protein(n, 1, seed=1200 + i) for i, n in enumerate(lengths)]
+    batches, infos = [synthetic.collate(p) for p in prots], [p.info for p in prots]
+    bm = sampler.Backmapper(weights.init_denoiser_state(0), weights.init_vae_decode_state(0), "N6", num_sampling_steps=8, precision="f16")
+    sb = sampler.ShardedBackmapper(bm, 0, 1, max_frames=3, max_pad=0.12)
+    groups = sb.local_groups(sb.plan(lengths, 2)[0], lengths)
+    assert len(groups) >= 2 and sorted(f for g in groups for f in g[0]) == list(range(5))
+    out = sb.backmap(batches, infos, 2, generator=torch.Generator(device="cuda").manual_seed(5))
+    assert sorted(out) == [(f, e) for f in range(5) for e in range(2)]
+    for (f, e), xyz in out.items():
+        permute, atom_idx, _ = infos[f]
+        assert xyz.shape == (permute.numel(), 3) and torch.isfinite(xyz).all()
+        ca_rows = torch.nonzero(atom_idx[permute] % 14 == 3)[:, 0]
+        assert ca_rows.numel() == lengths[f]
+        assert torch.equal(xyz[ca_rows], prots[f].ca_full[0, 1:-1]), (f, e)
+    assert not torch.equal(out[(0, 0)], out[(0, 1)])                      # members differ (their own noise)
+    again = sb.backmap(batches, infos, 2, generator=torch.Generator(device="cuda").manual_seed(5))
+    assert all(torch.equal(out[k], again[k]) for k in out)                # same seeds, same result

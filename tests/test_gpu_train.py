@@ -49,6 +49,69 @@ def test_gemm_against_float64(M, N, K, a_kc, b_kc):
         assert err < 2e-6 * max(1.0, K / 1000) ** 0.5, (acc, err)
 
 
+@pytest.mark.parametrize("M,N,K,a_kc,b_kc", [(4096, 128, 128, 1, 1), (5000, 512, 128, 1, 1), (3001, 128, 512, 1, 1), (2000, 1152, 128, 1, 1),
+                                             (4100, 128, 152, 1, 1), (128, 128, 16384, 0, 0), (512, 128, 70001, 0, 0), (128, 512, 9000, 0, 0)])
+def test_gemm_tf32_tensor_cores_against_float64(M, N, K, a_kc, b_kc):
+    """cb2t_gemm in TF32 mode (tcgen05.mma kind::tf32): the K-major form (forward / data gradient) with M, N, K tails, and the MN-major form
+    (weight gradient: 32-byte-atom swizzle, split reduction).  Bar 2e-3 of the largest output (TF32 rounds operands to 10 mantissa bits;
+    measured 7-9e-4)."""
+    from codlad_b200 import _native as Nn
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((M, K) if a_kc else (K, M), generator=g)
+    B = torch.randn((N, K) if b_kc else (K, N), generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    ref = (A.double() if a_kc else A.double().t()) @ (B.double().t() if b_kc else B.double())
+    Ad, Bd, Cd = A.cuda(), B.cuda(), C0.cuda().clone()
+    try:
+        Nn.check(Nn.lib().cb2t_set_gemm_mode(1))
+        for acc in (0, 1):
+            Cd.copy_(C0)
+            Nn.check(Nn.lib().cb2t_gemm(Ad.data_ptr(), Bd.data_ptr(), Cd.data_ptr(), M, N, K, A.shape[1], B.shape[1], N, a_kc, b_kc, acc, Nn.stream_ptr()))
+            want = ref + (C0.double() if acc else 0)
+            err = float((Cd.cpu().double() - want).abs().max() / want.abs().max())
+            assert 1e-5 < err < 2e-3, (acc, err)          # > 1e-5: the tensor-core path really ran (fp32 SIMT would be ~5e-7)
+    finally:
+        Nn.check(Nn.lib().cb2t_set_gemm_mode(0))
+
+
+def test_denoiser_gradients_tf32_mode(R):
+    """The same backward with the large GEMMs on the tensor cores in TF32 -- the arithmetic the reference trains with (train_latent.py:24-25).
+    Against fp32 autograd every gradient tensor stays within 1e-2 of its norm (measured ~2e-3), the model output within 5e-3."""
+    from codlad_b200 import train
+    sd = weights.init_denoiser_state(7)
+    lengths = [72, 66, 70]
+    batch, X, z, mask = _ragged_batch(lengths, 600)
+    B, L = mask.shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, L, 3, generator=g)
+    t = torch.tensor([999, 412, 3])
+    dout = torch.randn(B, L, 6, generator=g) * mask[..., None]
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        out_ref = R.denoiser_forward(leaves, x, t, X, z, mask, 64)
+        (out_ref * dout).sum().backward()
+    tr = train.DenoiserTrainer(sd, gemm="tf32")
+    try:
+        geom = train.Geometry(batch, 64, tr.device)
+        out = tr.forward(x.cuda(), t.cuda(), geom)
+        assert float((out.cpu() - out_ref.detach())[mask].abs().max()) < 5e-3
+        tr.zero_grad()
+        tr.backward(dout.cuda())
+    finally:
+        N_ = __import__("codlad_b200._native", fromlist=["x"])
+        N_.check(N_.lib().cb2t_set_gemm_mode(0))
+    worst = ("", 0.0)
+    for k, leaf in leaves.items():
+        ref = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+        got = tr.grads[k].cpu()
+        if k == "features.embeddings.linear.weight":
+            ref, got = ref[:, :65], got[:, :65]
+        err = float((got - ref).norm()) / (float(ref.norm()) + 1e-12)
+        worst = max(worst, (k, err), key=lambda kv: kv[1])
+        assert err < 1e-2, (k, err)
+    print(f"tf32 mode: worst gradient error {worst[1]:.2e} ({worst[0]})")
+
+
 @pytest.mark.parametrize("lengths,kn", [([40, 33], 64), ([72, 66, 70], 64), ([50], 32)])
 def test_denoiser_gradients_match_autograd_on_the_oracle(R, lengths, kn):
     """Every one of the 108 parameter gradients of the WHOLE denoiser (3 encoder layers with node message, FFN and edge update, 3 decoder
