@@ -368,7 +368,7 @@ def run_train(args):
             "config": {"workload": "configs[4]: train_latent denoiser fwd+bwd, batch 128, PED-like ragged lengths U[60,400], dropout 0.6, DDP NCCL all-reduce",
                        "per_rank_batch": per, "micro_batch": micro, "padded_residues_per_rank": padded, "residues": residues},
             "loss": losses, "grad_norm": tr.grad_norm(), "achieved_tflops": flops / (ms * 1e-3) / 1e12,
-            "fp32_nominal_peak_tflops": FP32_NOMINAL_TFLOPS * world, "cpu_baseline": cpu,
+            "fp32_nominal_peak_tflops": FP32_NOMINAL_TFLOPS * world, "tf32_nominal_dense_peak_tflops": 1130.0 * world, "cpu_baseline": cpu,
         }))
     D.shutdown()
 
