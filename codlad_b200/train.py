@@ -320,8 +320,26 @@ class DenoiserTrainer:
         ctx[p] = dict(hV=hV, hsum=hsum, Z1=Z1, X1=X1, st1=st1, X2=X2, st2=st2, d1=d1, d2=d2)
         return hV2
 
-    def forward(self, x, t, geom: Geometry, dropout_p: float = 0.0, generator=None):
-        """x [B, L, 3] fp32, t [B] (original 0..999 scale) -> model output [B, L, 6]; the activations the backward needs are kept."""
+    def edge_features(self, g: Geometry, ctx: dict):
+        """CA_ProteinFeatures' trainable half + W_e (protein_mpnn_utils.py:511-523, latent_model.py:216) on the raw features of `g`:
+        positional table through edge_embedding[:, :16], raw features through [:, 16:], affine LayerNorm, W_e -> h_E0 [E, 128]."""
+        o, P = self.ops, self.params
+        Wp, bp, We = P["features.embeddings.linear.weight"], P["features.embeddings.linear.bias"], P["features.edge_embedding.weight"]
+        posT = (Wp[:, :65].t() + bp[None, :]).contiguous()                                # [65, 16]  (class 65 is never produced)
+        PT = o.linear(posT, We, 0, 16)                                                    # [65, 128]
+        Epre = o.linear(g.raw, We, 16, 151)
+        N.check(o.lib.cb2t_row_gather_add(_p(Epre), _p(PT), _p(g.pos_class), g.E, N.stream_ptr()), "row_gather_add")
+        lnw, lnb = P["features.norm_edges.weight"], P["features.norm_edges.bias"]
+        lnw1 = (lnw - 1.0).contiguous()
+        Efeat, _, stE = o.ln_mod(Epre, None, None, g.E, lnb.data_ptr(), lnw1.data_ptr(), None, 0, None, eps=1e-5)
+        hE = o.linear(Efeat, P["W_e.weight"], 0, H)
+        o.bias_gelu(hE, P["W_e.bias"], want_act=False)
+        ctx["feat"] = (posT, Epre, stE, Efeat, lnw1)
+        return hE
+
+    def forward(self, x, t, geom: Geometry, dropout_p: float = 0.0, generator=None, hE0=None, hS2=None, keep: bool = True):
+        """x [B, L, 3] fp32, t [B] (original 0..999 scale) -> model output [B, L, 6].  Training: the activations the backward needs are
+        kept (keep=True).  Inference (tf32_tier.py): hE0 / hS2 are the per-frame quantities hoisted out of the step loop, keep=False."""
         o, P, g = self.ops, self.params, geom
         self._set_mode()
         ctx = {"geom": g}
@@ -336,26 +354,16 @@ class DenoiserTrainer:
         o.bias_gelu(c, P["t_embedder.mlp.2.bias"], want_act=False)
         c_silu = o.ew(0, c)
         ctx["temb"] = (tf, T0, T0a, c, c_silu)
-        # edge features: positional table through edge_embedding[:, :16], raw features through [:, 16:], affine LayerNorm, W_e
-        Wp, bp, We = P["features.embeddings.linear.weight"], P["features.embeddings.linear.bias"], P["features.edge_embedding.weight"]
-        posT = (Wp[:, :65].t() + bp[None, :]).contiguous()                                # [65, 16]  (class 65 is never produced)
-        PT = o.linear(posT, We, 0, 16)                                                    # [65, 128]
-        Epre = o.linear(g.raw, We, 16, 151)
-        N.check(o.lib.cb2t_row_gather_add(_p(Epre), _p(PT), _p(g.pos_class), g.E, N.stream_ptr()), "row_gather_add")
-        lnw, lnb = P["features.norm_edges.weight"], P["features.norm_edges.bias"]
-        lnw1 = (lnw - 1.0).contiguous()
-        Efeat, _, stE = o.ln_mod(Epre, None, None, g.E, lnb.data_ptr(), lnw1.data_ptr(), None, 0, None, eps=1e-5)
-        hE = o.linear(Efeat, P["W_e.weight"], 0, H)
-        o.bias_gelu(hE, P["W_e.bias"], want_act=False)
-        ctx["feat"] = (posT, Epre, stE, Efeat, lnw1)
+        hE = hE0 if hE0 is not None else self.edge_features(g, ctx)
         hV = o.linear(x2, P["x_in.weight"], 0, 3)
         o.bias_gelu(hV, P["x_in.bias"], want_act=False)
         ctx["x2"] = x2
         for l in range(3):
             hV, hE = self._enc_layer(l, hV, hE, c_silu, g, ctx, dropout_p, generator)
         hVenc = hV
-        hS = P["W_s.weight"][g.cg_z.reshape(-1).long()]                                   # embedding lookup (index plumbing), latent_model.py:225
-        hS2 = o.ew(3, hS.contiguous(), scale=2.0)
+        if hS2 is None:
+            hS = P["W_s.weight"][g.cg_z.reshape(-1).long()]                               # embedding lookup (index plumbing), latent_model.py:225
+            hS2 = o.ew(3, hS.contiguous(), scale=2.0)
         hE2x = o.ew(3, hE, scale=2.0)
         ctx["dec_in"] = (hE, hS2, hE2x, hVenc)
         for l in range(3):
@@ -366,7 +374,7 @@ class DenoiserTrainer:
         out = o.linear(Yf, P["W_out.linear.weight"], 0, H)
         o.bias_gelu(out, P["W_out.linear.bias"], want_act=False)
         ctx["final"] = (hV, stF, Yf)
-        self.ctx = ctx
+        self.ctx = ctx if keep else None
         return out.view(g.B, g.L, 6)
 
     # ------------------------------------------------------------------------------------------------------------ backward
