@@ -50,6 +50,8 @@ SIGNATURES = {
     "cb2_ic_to_xyz": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "cb2_superposed_rmsd": (_I, [_P, _P, _P, _I, _P, _P]),
     "cb2_eval_bond_graphs": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, C.c_float, _P, _P, _P]),
+    "cb2_pair_losses": (_I, [_P, _P, _P, _I, C.c_longlong, C.c_float, C.c_float, _P, _P]),
+    "cb2_keys_once": (_I, [_P, C.c_longlong, _P, _P]),
 }
 
 # include/codlad_b200_train.h (the train_latent step)

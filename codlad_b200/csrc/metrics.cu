@@ -155,6 +155,76 @@ __global__ void __launch_bounds__(256) superposed_rmsd_kernel(const float* __res
     out[s] = sqrt(fmax(0.0, (Ga + Gb - 2.0 * lam) / n));
 }
 
+
+// Pair-list losses of the evaluation step (test.py:97-146: inter_result, clash_result, ged_result).  One row of `idx` is either a pair
+// (a, b): d = sqrt(|x_a - x_b|^2 + EPS), or a quad (a, b, c, e): d = distance of the ring centres (x_a + x_b)/2 and (x_c + x_e)/2
+// (pi-pi stacking).  Per row: [d < thr_count], max(d - thr_hinge, 0), (d - d_data)^2 with d_data the same distance in `xyz_data`.
+// fp32 distances in the reference's operation order; the three sums are accumulated in double, per CTA and then over CTAs in a
+// fixed order (deterministic).
+constexpr int PL_THREADS = 256, PL_MAX_BLOCKS = 592;
+constexpr float PL_EPS = 1e-7f;                          // test.py:27
+
+__device__ __forceinline__ float pair_dist(const float* __restrict__ x, const long long* __restrict__ row, int width) {
+    float d2 = 0.f;
+    if (width == 2) {
+        const float *a = x + row[0] * 3, *b = x + row[1] * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float d = __fsub_rn(a[k], b[k]); d2 = __fadd_rn(d2, __fmul_rn(d, d)); }
+    } else {
+        const float *a = x + row[0] * 3, *b = x + row[1] * 3, *c = x + row[2] * 3, *e = x + row[3] * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float d = __fsub_rn(__fdiv_rn(__fadd_rn(a[k], b[k]), 2.f), __fdiv_rn(__fadd_rn(c[k], e[k]), 2.f));
+            d2 = __fadd_rn(d2, __fmul_rn(d, d));
+        }
+    }
+    return __fsqrt_rn(__fadd_rn(d2, PL_EPS));
+}
+
+__global__ void __launch_bounds__(PL_THREADS) pair_losses_kernel(const float* __restrict__ xyz, const float* __restrict__ xyz_data,
+                                                                 const long long* __restrict__ idx, int width, long long P, float thr_count,
+                                                                 float thr_hinge, double* __restrict__ part) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long r = (long long)blockIdx.x * PL_THREADS + threadIdx.x; r < P; r += (long long)gridDim.x * PL_THREADS) {
+        const long long* row = idx + r * width;
+        const float d = pair_dist(xyz, row, width);
+        acc[0] += d < thr_count ? 1.0 : 0.0;
+        acc[1] += (double)fmaxf(__fsub_rn(d, thr_hinge), 0.f);
+        if (xyz_data != nullptr) { const float e = __fsub_rn(d, pair_dist(xyz_data, row, width)); acc[2] += (double)__fmul_rn(e, e); }
+    }
+    __shared__ double red[3][PL_THREADS / 32];
+    for (int k = 0; k < 3; ++k) {
+        double v = acc[k];
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < PL_THREADS / 32; ++w) t += red[threadIdx.x][w];
+        part[blockIdx.x * 3 + threadIdx.x] = t;
+    }
+}
+
+__global__ void pair_losses_reduce_kernel(const double* __restrict__ part, int blocks, long long P, double* __restrict__ out) {
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int b = 0; b < blocks; ++b) t += part[b * 3 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 3) out[3] = (double)P;
+}
+
+// rows of a SORTED key list that occur exactly once (the `uniques[counts == 1]` of clash_result, test.py:121-123)
+__global__ void keys_once_kernel(const long long* __restrict__ keys, long long n, unsigned char* __restrict__ once) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long k = keys[i];
+    once[i] = ((i == 0 || keys[i - 1] != k) && (i + 1 == n || keys[i + 1] != k)) ? 1 : 0;
+}
+
+double* g_pl_part = nullptr;
+
 }  // namespace
 
 }  // namespace cb2
@@ -185,6 +255,30 @@ extern "C" int cb2_eval_bond_graphs(const float* xyz_ref, const float* xyz_gen, 
         CB2_LAUNCH_CHECK();
     }
     rmsd_sums_kernel<<<n_struct, 256, 0, s>>>(xyz_ref, xyz_gen, atomic_num, offsets, sums);
+    CB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cb2_pair_losses(const float* xyz, const float* xyz_data, const long long* idx, int width, long long n_rows, float thr_count,
+                               float thr_hinge, double* out4, void* stream) {
+    using namespace cb2;
+    if (!xyz || !out4 || (n_rows > 0 && !idx) || (width != 2 && width != 4) || n_rows < 0) { set_error("pair_losses: bad argument"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!g_pl_part) CB2_CUDA(cudaMalloc(&g_pl_part, (size_t)PL_MAX_BLOCKS * 3 * sizeof(double)));
+    int blocks = (int)((n_rows + PL_THREADS - 1) / PL_THREADS);
+    blocks = blocks < 1 ? 1 : (blocks > PL_MAX_BLOCKS ? PL_MAX_BLOCKS : blocks);
+    pair_losses_kernel<<<blocks, PL_THREADS, 0, s>>>(xyz, xyz_data, idx, width, n_rows, thr_count, thr_hinge, g_pl_part);
+    CB2_LAUNCH_CHECK();
+    pair_losses_reduce_kernel<<<1, 32, 0, s>>>(g_pl_part, blocks, n_rows, out4);
+    CB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cb2_keys_once(const long long* sorted_keys, long long n, unsigned char* once, void* stream) {
+    using namespace cb2;
+    if (n < 0 || (n > 0 && (!sorted_keys || !once))) { set_error("keys_once: bad argument"); return 1; }
+    if (n == 0) return 0;
+    keys_once_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sorted_keys, n, once);
     CB2_LAUNCH_CHECK();
     return 0;
 }

@@ -1,7 +1,7 @@
 """Sample-quality metrics of the evaluation step that follows sampling: the reference's
 `eval_sample_qualities` (utils/protein_module.py:335-364) and `valid_ratio_and_cut_off_result` (test.py:168-188) on the
-GPU.  The O(Na^2) bond-graph comparison and the RMSD sums run in libcodlad_b200.so (`cb2_eval_bond_graphs`); the elementwise
-losses of test.py:97-166 are restated with torch ops on whatever device their inputs live on.
+GPU.  The O(Na^2) bond-graph comparison and the RMSD sums run in libcodlad_b200.so (`cb2_eval_bond_graphs`); the pair-list
+losses of test.py:97-146 reduce in `cb2_pair_losses`; xyz / internal-coordinate losses (test.py:148-166) are torch elementwise ops.
 """
 from __future__ import annotations
 
@@ -115,14 +115,45 @@ def compute_div(gen_structures, ref_structure):
     return float(1.0 - rmsd_gen / rmsd_ref), float(rmsd_ref), float(rmsd_gen)
 
 
-# -- elementwise evaluation losses (test.py:97-166); torch ops on the inputs' device ------------------------------------------
-def _pair_dist(xyz, pairs):
-    return ((xyz[pairs[:, 0]] - xyz[pairs[:, 1]]).pow(2).sum(-1) + EPS).sqrt()
+# -- pair-list evaluation losses (test.py:97-151) -------------------------------------------------------------------------------
+def pair_losses(xyz, idx, xyz_data=None, thr_count: float = 0.0, thr_hinge: float = 0.0) -> torch.Tensor:
+    """`cb2_pair_losses`: [4] float64 on the device = {#(d < thr_count), sum max(d - thr_hinge, 0), sum (d - d_data)^2, rows} over
+    the pair ([P, 2]) or centre-pair ([P, 4]) list `idx`."""
+    N.require_cuda()
+    dev = xyz.device if xyz.is_cuda else torch.device("cuda")
+    x = xyz.to(dev, torch.float32).contiguous()
+    xd = None if xyz_data is None else xyz_data.to(dev, torch.float32).contiguous()
+    ix = idx.to(dev, torch.int64).contiguous()
+    if ix.dim() != 2 or ix.shape[1] not in (2, 4):
+        raise ValueError("idx must be [P, 2] or [P, 4]")
+    if ix.numel() and (int(ix.min()) < 0 or int(ix.max()) >= x.shape[0]):
+        raise IndexError("pair index out of range")
+    if xd is not None and xd.shape != x.shape:
+        raise ValueError("xyz_data must have the shape of xyz")
+    out = torch.empty(4, dtype=torch.float64, device=dev)
+    N.check(N.lib().cb2_pair_losses(N.dptr(x), N.dptr(xd) if xd is not None else None, N.dptr(ix) if ix.numel() else None, int(ix.shape[1]),
+                                    int(ix.shape[0]), C.c_float(thr_count), C.c_float(thr_hinge), N.dptr(out), N.stream_ptr()), "pair_losses")
+    return out
+
+
+def rows_once(a: torch.Tensor, b: torch.Tensor, n_atoms: int) -> torch.Tensor:
+    """Rows of cat(a, b) ([*, 2] index pairs) that occur exactly once, in lexicographic order -- `uniques[counts == 1]` of
+    test.py:120-123 -- on the device: int64 keys, one sort, `cb2_keys_once`."""
+    N.require_cuda()
+    dev = a.device if a.is_cuda else torch.device("cuda")
+    rows = torch.cat((a.to(dev, torch.int64), b.to(dev, torch.int64)))
+    keys = torch.sort(rows[:, 0] * int(n_atoms) + rows[:, 1]).values.contiguous()
+    once = torch.empty(keys.numel(), dtype=torch.uint8, device=dev)
+    N.check(N.lib().cb2_keys_once(N.dptr(keys) if keys.numel() else None, int(keys.numel()), N.dptr(once) if keys.numel() else None,
+                                  N.stream_ptr()), "keys_once")
+    k = keys[once.bool()]
+    return torch.stack((k // int(n_atoms), k % int(n_atoms)), 1)
 
 
 def ged_result(xyz_recon, xyz, edge_list):
     """test.py:141-146: mean squared difference of the bonded distances."""
-    return (_pair_dist(xyz_recon, edge_list) - _pair_dist(xyz, edge_list)).pow(2).mean()
+    o = pair_losses(xyz_recon, edge_list, xyz_data=xyz)
+    return (o[2] / o[3]).float()
 
 
 def xyz_result(xyz_recon, xyz):
@@ -130,16 +161,34 @@ def xyz_result(xyz_recon, xyz):
     return (xyz_recon - xyz).pow(2).sum(-1).mean()
 
 
-def clash_result(edge_list, nbr_list, xyz_recon, bb_NO_list):
+def clash_result(edge_list, nbr_list, xyz_recon, bb_NO_list, non_bonded=None):
     """test.py:118-139: fraction of non-bonded neighbour pairs (rows occurring once in cat(edge_list, nbr_list)) closer than
-    1.2 A plus the same fraction over the backbone N-O pairs."""
-    combined = torch.cat((edge_list, nbr_list))
-    uniques, counts = combined.unique(dim=0, return_counts=True)
-    d = _pair_dist(xyz_recon, uniques[counts == 1])
-    zero = torch.zeros((), device=xyz_recon.device)
-    loss = (d < 1.2).sum().float() / d.numel() if d.numel() > 0 else zero
-    b = _pair_dist(xyz_recon, bb_NO_list)
-    return loss + ((b < 1.2).sum().float() / b.numel() if b.numel() > 0 else zero)
+    1.2 A plus the same fraction over the backbone N-O pairs.  `non_bonded`: that pair list if the caller kept it from an earlier
+    call (it depends on the topology only)."""
+    if non_bonded is None:
+        non_bonded = rows_once(edge_list, nbr_list, xyz_recon.shape[0])
+    a = pair_losses(xyz_recon, non_bonded, thr_count=1.2)
+    b = pair_losses(xyz_recon, bb_NO_list.reshape(-1, 2), thr_count=1.2)
+    frac = lambda o: (o[0] / o[3]).float() if float(o[3]) > 0 else torch.zeros((), device=o.device)
+    return frac(a) + frac(b)
+
+
+def inter_result(interaction_list, pi_pi_list, xyz_recon):
+    """test.py:97-116: hinge losses on the side-chain interaction pairs (beyond 4 A) and on the pi-pi ring-centre pairs (beyond 6 A),
+    weighted by their share of the interactions.  Returns (loss_inter, loss_pi_pi) like the reference (loss_inter includes the
+    weighted pi-pi term)."""
+    n_i, n_p = int(interaction_list.shape[0]), int(pi_pi_list.shape[0])
+    dev = xyz_recon.device if xyz_recon.is_cuda else torch.device("cuda")
+    loss_inter = torch.zeros((), device=dev)
+    loss_pp = torch.zeros((), device=dev)
+    if n_i > 0:
+        o = pair_losses(xyz_recon, interaction_list, thr_hinge=4.0)
+        loss_inter = (o[1] / o[3]).float() * (n_i / (n_i + n_p))
+    if n_p > 0:
+        o = pair_losses(xyz_recon, pi_pi_list, thr_hinge=6.0)
+        loss_pp = (o[1] / o[3]).float()
+        loss_inter = loss_inter + loss_pp * (n_p / (n_i + n_p))
+    return loss_inter, loss_pp
 
 
 def recon_result(ic_recon, ic, mask_):

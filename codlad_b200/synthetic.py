@@ -116,3 +116,18 @@ def collate_many(proteins, frame: int = 0) -> dict:
 
 def latent_noise(shape, seed: int) -> torch.Tensor:
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def eval_loss_case(seed: int, na: int = 3000) -> dict:
+    """Seeded inputs of the pair-list losses (shared with the tests): a compact random structure (so that the 1.2 A clash threshold
+    is exercised), a noisy copy, bond / neighbour / backbone N-O / interaction pair lists and pi-pi quads."""
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.randn(na, 3, generator=g) * 2.5
+    recon = xyz + 0.2 * torch.randn(na, 3, generator=g)
+    edge = torch.randint(0, na, (5000, 2), generator=g)
+    nbr = torch.cat([edge[:1500], edge[100:200].flip(1), torch.randint(0, na, (20000, 2), generator=g)])
+    nbr = torch.cat([nbr, nbr[-50:]])
+    bb = torch.randint(0, na, (700, 2), generator=g)
+    inter = torch.randint(0, na, (400, 2), generator=g)
+    pipi = torch.randint(0, na, (37, 4), generator=g)
+    return dict(xyz=xyz, recon=recon, edge=edge, nbr=nbr, bb=bb, inter=inter, pipi=pipi)

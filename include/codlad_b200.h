@@ -164,6 +164,17 @@ CB2_API int cb2_eval_bond_graphs(const float* xyz_ref, const float* xyz_gen, con
  * mdtraj is absent from the build container: parity is against a float64 Kabsch (SVD) restatement, i.e. unpinned against mdtraj itself. */
 CB2_API int cb2_superposed_rmsd(const float* A, const float* B, const long long* offsets, int n_struct, double* out, void* stream);
 
+/* Replaces: the pair-list reductions of inter_result / clash_result / ged_result (test.py:97-146).  xyz [Na, 3] DEVICE; xyz_data the
+ * reference coordinates (DEVICE) or NULL; idx [n_rows, width] int64 DEVICE, width 2 = atom pairs, width 4 = (a, b, c, e) quads whose
+ * distance is between the centres (x_a + x_b)/2 and (x_c + x_e)/2 (pi-pi stacking, test.py:113-116).  d = sqrt(|.|^2 + 1e-7) in fp32.
+ * out4 (DEVICE, double): {#(d < thr_count), sum max(d - thr_hinge, 0), sum (d - d_data)^2 (0 without xyz_data), n_rows}. */
+CB2_API int cb2_pair_losses(const float* xyz, const float* xyz_data, const long long* idx, int width, long long n_rows, float thr_count,
+                    float thr_hinge, double* out4, void* stream);
+
+/* Replaces: the `uniques[counts == 1]` selection of clash_result (test.py:121-123) on a SORTED int64 key list (key = a * Na + b):
+ * once[i] = 1 where the key occurs exactly once.  DEVICE pointers. */
+CB2_API int cb2_keys_once(const long long* sorted_keys, long long n, unsigned char* once, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

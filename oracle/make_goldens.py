@@ -295,7 +295,28 @@ def golden_sample_qualities(name, L, frames, seed, sigma):
     print(name, np.array(out).round(4).tolist())
 
 
+def golden_eval_losses(name, seed):
+    """inter_result / clash_result / ged_result of the unmodified reference (test.py:97-146).  test.py itself cannot be imported here
+    (mdtraj, ase, torchdiffeq are absent), so the three function definitions are taken from its syntax tree and executed as they are."""
+    import ast
+    src = open(os.path.join(ref_stubs.REFERENCE_ROOT, "test.py")).read()
+    want = ("inter_result", "clash_result", "ged_result")
+    mod = ast.Module(body=[n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want], type_ignores=[])
+    ns = {"torch": torch, "EPS": 1e-7}
+    exec(compile(mod, "reference/test.py", "exec"), ns)
+    c = synthetic.eval_loss_case(seed)
+    li, lp = ns["inter_result"](c["inter"], c["pipi"], c["recon"])
+    li0, _ = ns["inter_result"](c["inter"], c["pipi"][:0], c["recon"])
+    clash = ns["clash_result"](c["edge"], c["nbr"], c["recon"], c["bb"])
+    ged = ns["ged_result"](c["recon"], c["xyz"], c["edge"])
+    u, cnt = torch.cat((c["edge"], c["nbr"])).unique(dim=0, return_counts=True)
+    vals = np.array([float(li), float(lp), float(li0), float(clash), float(ged), float((cnt == 1).sum())], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), vals=vals, meta=np.array([seed]))
+    print(name, vals.tolist())
+
+
 GOLDENS = {
+    "eval_losses": lambda n: golden_eval_losses(n, 8101),
     "denoiser_L64_B1": lambda n: golden_denoiser(n, 64, 1, 64, 1001, 2001, [717]),
     "denoiser_L70_B2": lambda n: golden_denoiser(n, 70, 2, 64, 1002, 2002, [999, 10]),
     "denoiser_L100_K48": lambda n: golden_denoiser(n, 100, 1, 48, 1004, 2004, [505]),

@@ -562,3 +562,46 @@ def compute_div(gen_structures, ref_structure):
     r_ref = np.mean([superposed_rmsd(gen[i][p], ref[p]) for i in range(gen.shape[0]) for p in range(gen.shape[1])])
     r_gen = np.mean([superposed_rmsd(gen[i][p], mean_gen[p]) for i in range(gen.shape[0]) for p in range(gen.shape[1])])
     return 1.0 - r_gen / r_ref, r_ref, r_gen
+
+
+# ---------------------------------------------------------------------------------------------- pair-list evaluation losses
+EVAL_EPS = 1e-7                                                     # test.py:27
+
+
+def _pd(xyz, pairs):
+    return ((xyz[pairs[:, 0]] - xyz[pairs[:, 1]]).pow(2).sum(-1) + EVAL_EPS).sqrt()
+
+
+def inter_result(interaction_list, pi_pi_list, xyz_recon):
+    """test.py:97-116."""
+    n_inter, n_pi = interaction_list.shape[0], pi_pi_list.shape[0]
+    tot = n_inter + n_pi
+    loss_inter = torch.tensor(0.0)
+    loss_pi = torch.tensor(0.0)
+    if n_inter > 0:
+        loss_inter = torch.clamp_min(_pd(xyz_recon, interaction_list) - 4.0, 0.0).mean() * (n_inter / tot)
+    if n_pi > 0:
+        c0 = (xyz_recon[pi_pi_list[:, 0]] + xyz_recon[pi_pi_list[:, 1]]) / 2
+        c1 = (xyz_recon[pi_pi_list[:, 2]] + xyz_recon[pi_pi_list[:, 3]]) / 2
+        loss_pi = torch.clamp_min(((c0 - c1).pow(2).sum(-1) + EVAL_EPS).sqrt() - 6.0, 0.0).mean()
+        loss_inter = loss_inter + loss_pi * (n_pi / tot)
+    return loss_inter, loss_pi
+
+
+def clash_pairs(edge_list, nbr_list):
+    """test.py:120-123: rows occurring exactly once in the concatenation."""
+    u, c = torch.cat((edge_list, nbr_list)).unique(dim=0, return_counts=True)
+    return u[c == 1]
+
+
+def clash_result(edge_list, nbr_list, xyz_recon, bb_NO_list):
+    """test.py:118-139."""
+    d = _pd(xyz_recon, clash_pairs(edge_list, nbr_list))
+    loss = (d < 1.2).sum().float() / d.numel() if d.numel() > 0 else torch.tensor(0.0)
+    b = _pd(xyz_recon, bb_NO_list)
+    return loss + ((b < 1.2).sum().float() / b.numel() if b.numel() > 0 else torch.tensor(0.0))
+
+
+def ged_result(xyz_recon, xyz, edge_list):
+    """test.py:141-146."""
+    return (_pd(xyz_recon, edge_list) - _pd(xyz, edge_list)).pow(2).mean()

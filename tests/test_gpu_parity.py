@@ -708,6 +708,38 @@ def test_superposed_rmsd_and_diversity_vs_oracle(R):
     assert abs(div - d0) < 1e-6 and abs(r_ref - a0) < 1e-5 * a0 and abs(r_gen - b0) < 1e-5 * b0
 
 
+def test_pair_list_losses_vs_reference(R):
+    """cb2_pair_losses / cb2_keys_once behind metrics.{inter,clash,ged}_result against the unmodified reference functions
+    (test.py:97-146; tests/golden/eval_losses.npz) and the oracle restatement.  The once-only pair selection is exact (duplicates
+    inside one list, pairs present in both lists, reversed pairs are distinct rows); the violation count is an integer and agrees
+    exactly; means agree to the reference's fp32 summation error (the kernel sums in double)."""
+    from codlad_b200 import metrics
+    gold = P.golden("eval_losses")
+    c = synthetic.eval_loss_case(int(gold["meta"][0]))
+    want = gold["vals"]
+    na = c["xyz"].shape[0]
+    cu = {k: v.cuda() for k, v in c.items()}
+    want_pairs = R.clash_pairs(c["edge"], c["nbr"])
+    got_pairs = metrics.rows_once(cu["edge"], cu["nbr"], na).cpu()
+    assert torch.equal(got_pairs, want_pairs) and got_pairs.shape[0] == int(want[5])
+    o = metrics.pair_losses(cu["recon"], want_pairs.cuda(), thr_count=1.2).cpu()
+    d = ((c["recon"][want_pairs[:, 0]] - c["recon"][want_pairs[:, 1]]).pow(2).sum(-1) + 1e-7).sqrt()
+    assert int(o[0]) == int((d < 1.2).sum()) and int(o[0]) > 10 and int(o[3]) == want_pairs.shape[0]
+    close = lambda a, b: abs(float(a) - float(b)) <= 3e-6 * max(abs(float(b)), 1e-3)
+    assert close(metrics.clash_result(cu["edge"], cu["nbr"], cu["recon"], cu["bb"]), want[3])
+    assert close(metrics.ged_result(cu["recon"], cu["xyz"], cu["edge"]), want[4])
+    gi, gp = metrics.inter_result(cu["inter"], cu["pipi"], cu["recon"])
+    assert close(gi, want[0]) and close(gp, want[1])
+    gi0, gp0 = metrics.inter_result(cu["inter"], cu["pipi"][:0], cu["recon"])
+    assert close(gi0, want[2]) and float(gp0) == 0.0
+    for il, pl in ((c["inter"][:0], c["pipi"]), (c["inter"][:0], c["pipi"][:0])):
+        gi, gp = metrics.inter_result(il.cuda(), pl.cuda(), cu["recon"])
+        wi, wp = R.inter_result(il, pl, c["recon"])
+        assert close(gi, wi) and close(gp, wp)
+    with pytest.raises(IndexError):
+        metrics.pair_losses(cu["xyz"], torch.tensor([[0, na]]).cuda())
+
+
 def test_repeated_frames_in_a_batch_share_their_precompute():
     """An ensemble written as repeated frames in the reference batch schema (and test.py's doubled batch) is served by a plan that holds the
     DISTINCT frames only; results equal those of one-frame batches row by row."""

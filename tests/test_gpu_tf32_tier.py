@@ -6,7 +6,7 @@ tier is NOT more accurate than the f16 tier (measured 7.4e-4 relative vs 4.8e-4)
 import pytest
 import torch
 
-import parity_utils as P
+from tests import parity_utils as P
 from codlad_b200 import synthetic, weights
 from codlad_b200.diffusion import create_diffusion
 

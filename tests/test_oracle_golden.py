@@ -157,3 +157,16 @@ def test_sample_quality_stats_against_reference_golden(name):
     np.testing.assert_allclose(((c[:, 1] - c[:, 2]).abs() / c[:, 1]).numpy(), q[:, 3], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(torch.sqrt(sums[:, 0] / sums[:, 1]).numpy(), q[:, 4], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(torch.sqrt(sums[:, 2] / sums[:, 3]).numpy(), q[:, 5], rtol=1e-6, atol=1e-9)
+
+
+def test_oracle_pair_list_losses_vs_reference():
+    """oracle.restate.{inter,clash,ged}_result against the unmodified reference functions (test.py:97-146, tests/golden/eval_losses.npz)."""
+    from oracle import restate as R
+    gold = P.golden("eval_losses")
+    c = synthetic.eval_loss_case(int(gold["meta"][0]))
+    want = gold["vals"]
+    li, lp = R.inter_result(c["inter"], c["pipi"], c["recon"])
+    li0, _ = R.inter_result(c["inter"], c["pipi"][:0], c["recon"])
+    got = [float(li), float(lp), float(li0), float(R.clash_result(c["edge"], c["nbr"], c["recon"], c["bb"])),
+           float(R.ged_result(c["recon"], c["xyz"], c["edge"])), float(R.clash_pairs(c["edge"], c["nbr"]).shape[0])]
+    assert np.allclose(got, want, rtol=1e-6, atol=0)
