@@ -166,6 +166,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                 const int slot = ti % N_SLOT;
                 mbar_wait(bar_full(slot), (uint32_t)((ti / N_SLOT) & 1));
                 tc_fence_after();
+                cmark(6);
                 // descriptors of k-step 0; a k-step advances only the (16-byte granular) start-address field
                 const uint64_t a0 = umma_desc(smem_u32(sW + slot * TILE_BYTES), 16, 1024), b0 = umma_desc(smem_u32(act_tile(act)), 16, 1024);
                 if (elect_one()) {
@@ -176,6 +177,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                     umma_commit(bar_free(slot));
                 }
                 __syncwarp();
+                cmark(7);
                 ++ti;
             };
             auto commit_phase = [&]() { if (elect_one()) umma_commit(bar_mma); __syncwarp(); cmark(4); };
@@ -186,7 +188,7 @@ __device__ __forceinline__ void node_block(unsigned char* smem, const uint32_t t
                 // completed, and its share of the output GEMM when its hidden tile is written (no phase-wide hand-offs)
                 wait_act();
                 for (int c = 0; c < 4; ++c) { gemm(1, R2 + c * NT, false); if (elect_one()) umma_commit(bar_chunk(c)); __syncwarp(); }
-                for (int c = 0; c < 4; ++c) { mbar_wait(bar_mid(c), 0); tc_fence_after(); gemm(2 + c, R3, c > 0); }
+                for (int c = 0; c < 4; ++c) { mbar_wait(bar_mid(c), 0); tc_fence_after(); cmark(8); gemm(2 + c, R3, c > 0); }
                 commit_phase();
             }
             if (p.n_proj > 0) {

@@ -20,7 +20,7 @@ a.record(); pl.forward_partial(x, t, stop); b.record(); torch.cuda.synchronize()
 print("partial forward us", a.elapsed_time(b) * 1e3)
 tr = pl.buffer("tc_trace").cpu().tolist()
 n = tr[512]
-cn = ["control start", "?", "operands ready", "?", "MMAs issued", "?"]
+cn = ["control start", "?", "operands ready", "?", "phase committed", "?", "  weight tile landed", "  gemm issued", "  hidden chunk ready"]
 prev = None; t0 = None
 for v in tr[513:513 + n]:
     v &= (1 << 64) - 1
