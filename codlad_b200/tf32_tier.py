@@ -39,6 +39,7 @@ class Tf32Denoiser:
         self.hE0 = self.tr.edge_features(self.geom, ctx)
         hS = self.tr.params["W_s.weight"][self.geom.cg_z.reshape(-1).long()].contiguous()
         self.hS2 = self.tr.ops.ew(3, hS, scale=2.0)
+        self.tr._set_mode(False)
         self._graph = None
 
     def forward(self, x, t):

@@ -227,8 +227,10 @@ class DenoiserTrainer:
                 else:
                     cur.copy_(w.t())
 
-    def _set_mode(self):
-        N.check(self.ops.lib.cb2t_set_gemm_mode(1 if self.gemm_mode == "tf32" else 0), "set_gemm_mode")
+    def _set_mode(self, on: bool = True):
+        """The GEMM arithmetic is a switch of the library (cb2t_set_gemm_mode), read when a GEMM is launched: set on entry of forward /
+        backward, back to the fp32 default on exit so that nothing else in the process inherits TF32."""
+        N.check(self.ops.lib.cb2t_set_gemm_mode(1 if (on and self.gemm_mode == "tf32") else 0), "set_gemm_mode")
 
     def state_dict(self, ema: bool = False):
         src = self.ema if ema else self.params
@@ -375,6 +377,7 @@ class DenoiserTrainer:
         o.bias_gelu(out, P["W_out.linear.bias"], want_act=False)
         ctx["final"] = (hV, stF, Yf)
         self.ctx = ctx if keep else None
+        self._set_mode(False)
         return out.view(g.B, g.L, 6)
 
     # ------------------------------------------------------------------------------------------------------------ backward
@@ -536,6 +539,7 @@ class DenoiserTrainer:
         dT0 = o.ew(1, T0, dT0a)
         self._lin_bwd(dT0, tf, "t_embedder.mlp.0", 0, 256, need_dx=False)
         self.ctx = None
+        self._set_mode(False)
 
     # ------------------------------------------------------------------------------------------------------------ optimiser
     def zero_grad(self):

@@ -41,6 +41,7 @@ def test_gemm_against_float64(M, N, K, a_kc, b_kc):
     C0 = torch.randn(M, N, generator=g)
     ref = (A.double() if a_kc else A.double().t()) @ (B.double().t() if b_kc else B.double())
     Ad, Bd, Cd = A.cuda(), B.cuda(), C0.cuda().clone()
+    Nn.check(Nn.lib().cb2t_set_gemm_mode(0))
     for acc in (0, 1):
         Cd.copy_(C0)
         Nn.check(Nn.lib().cb2t_gemm(Ad.data_ptr(), Bd.data_ptr(), Cd.data_ptr(), M, N, K, A.shape[1], B.shape[1], N, a_kc, b_kc, acc, Nn.stream_ptr()))
