@@ -71,10 +71,20 @@ def frames_from_batch(batch: dict, infos, num_ensemble: int = 1, frame_of=None) 
     members per frame (member order: ensemble-major, i.e. b = e*F + f), or with the explicit member list
     `frame_of` [NB] (frame index of every member; frames may then carry different member counts)."""
     num = batch["num_CGs"].to(torch.int64).cpu()
+    if num.numel() == 0:
+        raise ValueError("frames_from_batch: the batch holds no frames")
+    if int(num.min()) < 1:
+        raise ValueError("frames_from_batch: a frame with no residues")
+    if frame_of is None and int(num_ensemble) < 1:
+        raise ValueError("frames_from_batch: num_ensemble must be at least 1")
     F, L = num.numel(), int(num.max())
     cg = batch["CG_nxyz"].cpu().to(torch.float32)
     og = batch["OG_CG_nxyz"].cpu().to(torch.float32)
+    if cg.shape[0] != int(num.sum()) or og.shape[0] != int(num.sum()) + 2 * F:
+        raise ValueError("frames_from_batch: CG_nxyz / OG_CG_nxyz do not match num_CGs")
     shared = isinstance(infos, tuple) and len(infos) == 3 and torch.is_tensor(infos[0])
+    if not shared and len(infos) != F:
+        raise ValueError(f"frames_from_batch: {len(infos)} topology tuples for {F} frames")
     X, cg_z = batching.pad_frames(cg, num, L)
     ca_full = batching.pad_frames(og, num + 2, L + 2)[0]
     orders = torch.zeros(F, L, 10, 3, dtype=torch.int8)

@@ -127,6 +127,46 @@ def test_ensemble_members_share_frame(eng, R, denoiser):
     assert (out - ref).abs().max() < 5e-5
 
 
+@pytest.mark.parametrize("L,NB", [(2, 1), (3, 2), (8, 1), (17, 3), (31, 2)])
+def test_tiny_proteins_both_tiers_vs_oracle(eng, R, denoiser, L, NB):
+    """The smallest inputs the reference accepts (k = min(K, L) neighbours, protein_mpnn_utils.py:454; a tile holds more nodes than the
+    frame has): both tiers against the oracle forward, and k-NN exact."""
+    sd, den = denoiser
+    prot = synthetic.make_protein(L, 1, seed=900 + L)
+    X = prot.ca_full[:, 1:-1].contiguous()
+    z = prot.restype_full[1:-1][None]
+    x = synthetic.latent_noise((NB, L, 3), 19)
+    t = torch.linspace(0, 999, NB).round()
+    ref = R.denoiser_forward(sd, x, t.long(), X.expand(NB, -1, -1), z.expand(NB, -1), torch.ones(NB, L, dtype=torch.bool))
+    D_ref, I_ref = R.knn_graph(X, torch.ones(1, L), min(64, L))
+    for prec, bar in (("fp32", 5e-5), ("f16", 8e-3)):
+        plan = eng.Plan(den, 1, NB, L, prec)
+        plan.set_frames(X, torch.tensor([L]), z.int(), torch.zeros(NB, dtype=torch.int32))
+        assert torch.equal(plan.buffer("nbr_idx").cpu().long().reshape(1, L, -1), I_ref)
+        out = plan.forward(x.cuda(), t.cuda()).cpu()
+        assert torch.isfinite(out).all()
+        assert (out - ref).abs().max() < bar, (prec, float((out - ref).abs().max()))
+
+
+def test_empty_and_malformed_frame_sets_are_rejected():
+    """No frames / zero-length frames / mismatched topology lists raise before any kernel runs (the reference fails inside torch ops on
+    such batches; here the C ABI must never see them)."""
+    from codlad_b200 import sampler
+    prot = synthetic.make_protein(12, 1, seed=5)
+    batch = synthetic.collate(prot)
+    empty = {k: v[:0] for k, v in batch.items()}
+    with pytest.raises((ValueError, RuntimeError)):
+        sampler.frames_from_batch(empty, [], 1)
+    with pytest.raises((ValueError, RuntimeError)):
+        sampler.frames_from_batch(batch, [], 1)
+    bad = dict(batch)
+    bad["num_CGs"] = torch.tensor([0])
+    with pytest.raises((ValueError, RuntimeError)):
+        sampler.frames_from_batch(bad, [prot.info], 1)
+    with pytest.raises((ValueError, RuntimeError)):
+        sampler.frames_from_batch(batch, [prot.info], 0)
+
+
 # --------------------------------------------------------------------------------------- tcgen05 (fp16) tier
 @pytest.mark.parametrize("name,lengths", CASES)
 def test_denoiser_forward_f16_tier(eng, R, denoiser, name, lengths):
