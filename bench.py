@@ -540,7 +540,8 @@ def e2e_dropin(args, prot, batch, dev, steps):
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / steps
     return {"value": L_RES * ENSEMBLE / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-            "path": "MPNN_models factory + create_diffusion.p_sample_loop(model.forward) + get_norm_feature + VAE.latent_decode + ic_to_xyz (un-doubled 10-row batch)"}
+            "path": "MPNN_models factory + create_diffusion.p_sample_loop(model.forward) + get_norm_feature + VAE.latent_decode + ic_to_xyz (un-doubled 10-row batch)",
+            "scope": "ONE GPU (rank 0 alone), whatever --gpus is: compare with e2e / n_gpus"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
