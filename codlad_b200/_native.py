@@ -60,7 +60,9 @@ SIGNATURES.update({
     "cb2t_gemm": (_I, [_P, _P, _P, _I, _I, _I, _LL, _LL, _LL, _I, _I, _I, _P]),
     "cb2t_set_gemm_mode": (_I, [_I]),
     "cb2t_bias_gelu_fwd": (_I, [_P, _P, _LL, _I, _P, _P]),
+    "cb2t_linear_bias_gelu_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _LL, _LL, _LL, _P]),
     "cb2t_gelu_bwd": (_I, [_P, _P, _LL, _P, _P]),
+    "cb2t_gelu_bwd_colsum": (_I, [_P, _P, _LL, _I, _P, _P, _I, _P]),
     "cb2t_elementwise": (_I, [_I, _P, _P, _F, _LL, _P, _P]),
     "cb2t_edge_combine_gelu_fwd": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P, _P]),
     "cb2t_edge_gather_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),

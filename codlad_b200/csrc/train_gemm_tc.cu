@@ -7,8 +7,8 @@
 //   gemm_tc_tn    C[P,Q] (+)= A[R,P]^T B[R,Q]   both operands MN-contiguous: the weight gradient dW = dY^T X, a reduction over the R rows
 //                 (up to millions of edges) that is split over the grid and reduced in a fixed order.
 //
-// One persistent CTA per SM, 192 threads: warp 0 issues TMA loads into a ring of shared-memory stages (SWIZZLE_128B boxes of 32 fp32
-// = 128 bytes), warp 1 issues the MMAs (M = N = 128, K = 8 per instruction) into one of two 128-column TMEM accumulators, warps 2-5
+// One persistent CTA per SM, 320 threads: warp 0 issues TMA loads into a ring of shared-memory stages (SWIZZLE_128B boxes of 32 fp32
+// = 128 bytes), warp 1 issues the MMAs (M = N = 128, K = 8 per instruction) into one of two 128-column TMEM accumulators, warps 2-9
 // drain the other accumulator: tcgen05.ld -> swizzled staging tile in shared memory -> TMA store (or TMA reduce-add) of the 128 x 128
 // block, which also clips the M / N tails.  Tails of K are zero-filled by the TMA loads.
 #include <cstring>
@@ -25,7 +25,8 @@ using namespace tc;
 namespace {
 
 constexpr int TM = 128, TN = 128;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                               // two per TMEM lane quarter: each drains two of the four 32-column chunks
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int C_STAGE_BYTES = TM * TN * 4;                 // 64 KB staging of one output block (four 128-row x 128-byte sub-tiles)
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
@@ -65,13 +66,16 @@ struct GemmTcArgs {
     int accumulate;             // C += (TMA reduce-add) instead of C =
     int part_rows;              // TN with splits > 1: row pitch (in output rows) between partials inside the partial buffer map
     int tn_sbo, tn_layout;      // TN: descriptor stride between K groups and layout type (experiment switches)
+    int fuse;                   // NT only: 0 = C = A B^T; 1 = C = A B^T + bias; 2 = the same and Y = GELU(C) stored through mapY
+    int n_cols;                 // NT: N (guards the bias loads of a partial last column block)
 };
 
 // MODE 0 = NT (stage: A box {32 k, 128 m}, B box {32 k, 128 n}, K-major both, 32 k per stage, 4 MMAs)
 // MODE 1 = TN (stage: A = four boxes {32 p, 64 r}, B = four boxes {32 q, 64 r}, MN-major both, 64 r per stage, 8 MMAs)
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                             const __grid_constant__ CUtensorMap mapC, const GemmTcArgs g) {
+                                                             const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY,
+                                                             const float* __restrict__ bias, const GemmTcArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int STAGES = MODE == 0 ? 4 : 2;
     constexpr int OP_BYTES = MODE == 0 ? TM * 32 * 4 : 64 * 128 * 4;           // one operand of one stage: 16 KB (NT) / 32 KB (TN)
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -163,7 +167,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
-        const int q = warp & 3, r = q * 32 + lane;
+        const int q = warp & 3, r = q * 32 + lane;                      // (a warp reaches the TMEM lanes 32 (warp % 4) .. + 31)
+        const int half = (warp - 2) >> 2;                               // which two column chunks this warp drains
         const bool leader = warp == 2 && lane == 0;
         uint32_t nb = 0;
         for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++nb) {
@@ -173,30 +178,52 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             mbar_wait(bar_acc_full(ab), (nb >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 128);
+            // fused forward epilogue (NT): pass 0 stores Z = acc + bias, pass 1 re-reads the accumulator and stores Y = GELU(Z) -- the
+            // pre-activation and the activation of a Linear + GELU leave the kernel without a second trip through HBM
+            const int passes = (MODE == 0 && g.fuse == 2) ? 2 : 1;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32u(trow + (uint32_t)(c * 32), v);
-                unsigned char* dst = sC + c * (TM * 128) + r * 128;
+            for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll 1
+                for (int c = 2 * half; c < 2 * half + 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32u(trow + (uint32_t)(c * 32), v);
+                    if (MODE == 0 && g.fuse != 0) {
+                        const int col0 = nt * TN + c * 32;
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(ab));               // this accumulator may be overwritten
-            asm volatile("bar.sync 1, 128;" ::: "memory");               // the staging block is complete
-            if (leader) {
-                const int row0 = (g.splits > 1 ? z * g.part_rows : 0) + mt * TM;
-                for (int c = 0; c < 4; ++c) {
-                    if (g.accumulate) tma_reduce_add_2d(&mapC, nt * TN + c * 32, row0, smem_u32(sC + c * (TM * 128)));
-                    else tma_store_2d(&mapC, nt * TN + c * 32, row0, smem_u32(sC + c * (TM * 128)));
+                        for (int u = 0; u < 8; ++u) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col0 + 4 * u + 3 < g.n_cols) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4 * u));
+                            float z0 = __uint_as_float(v[4 * u]) + b.x, z1 = __uint_as_float(v[4 * u + 1]) + b.y;
+                            float z2 = __uint_as_float(v[4 * u + 2]) + b.z, z3 = __uint_as_float(v[4 * u + 3]) + b.w;
+                            if (pass == 1) { z0 = gelu_erf(z0); z1 = gelu_erf(z1); z2 = gelu_erf(z2); z3 = gelu_erf(z3); }
+                            v[4 * u] = __float_as_uint(z0); v[4 * u + 1] = __float_as_uint(z1);
+                            v[4 * u + 2] = __float_as_uint(z2); v[4 * u + 3] = __float_as_uint(z3);
+                        }
+                    }
+                    unsigned char* dst = sC + c * (TM * 128) + r * 128;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 }
-                tma_store_commit();
-                tma_store_wait_read();
+                fence_async_smem();
+                if (pass == passes - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_empty(ab));           // this accumulator may be overwritten
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");      // the staging block is complete
+                if (leader) {
+                    const int row0 = (g.splits > 1 ? z * g.part_rows : 0) + mt * TM;
+                    const CUtensorMap* out_map = pass == 0 ? &mapC : &mapY;
+                    for (int c = 0; c < 4; ++c) {
+                        if (g.accumulate) tma_reduce_add_2d(out_map, nt * TN + c * 32, row0, smem_u32(sC + c * (TM * 128)));
+                        else tma_store_2d(out_map, nt * TN + c * 32, row0, smem_u32(sC + c * (TM * 128)));
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read();
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");      // ... and has been read out: it may be refilled
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");               // ... and has been read out: it may be refilled
         }
         if (leader) tma_store_wait_all();
     }
@@ -266,9 +293,24 @@ int gemm_tc_nt(const float* A, const float* B, float* C, int M, int N, int K, lo
     if (int e = prepare()) return e;
     CUtensorMap mA, mB, mC;
     if (encode_f32_map(g_encode, &mA, A, M, K, lda, TM) || encode_f32_map(g_encode, &mB, B, N, K, ldb, TN) || encode_f32_map(g_encode, &mC, C, M, N, ldc, TM)) return 1;
-    GemmTcArgs g{(M + TM - 1) / TM, (N + TN - 1) / TN, (K + 31) / 32, 1, 0, accumulate, 0, 0, 0};
+    GemmTcArgs g{(M + TM - 1) / TM, (N + TN - 1) / TN, (K + 31) / 32, 1, 0, accumulate, 0, 0, 0, 0, N};
     const int blocks = g.tiles_m * g.tiles_n;
-    gemm_tc_kernel<0><<<blocks < g_sms ? blocks : g_sms, THREADS, smem_bytes<0>(), s>>>(mA, mB, mC, g);
+    gemm_tc_kernel<0><<<blocks < g_sms ? blocks : g_sms, THREADS, smem_bytes<0>(), s>>>(mA, mB, mC, mC, nullptr, g);
+    CB2_LAUNCH_CHECK();
+    return 0;
+}
+
+// Z[M,N] = A[M,K] B[N,K]^T + bias[N];  Y[M,N] = GELU(Z) when Y != nullptr (same pitch as Z)
+int gemm_tc_nt_bias_gelu(const float* A, const float* B, const float* bias, float* Z, float* Y, int M, int N, int K, long long lda, long long ldb,
+                         long long ldz, cudaStream_t s) {
+    if (int e = prepare()) return e;
+    CUtensorMap mA, mB, mZ, mY;
+    if (encode_f32_map(g_encode, &mA, A, M, K, lda, TM) || encode_f32_map(g_encode, &mB, B, N, K, ldb, TN) || encode_f32_map(g_encode, &mZ, Z, M, N, ldz, TM)) return 1;
+    if (Y != nullptr) { if (encode_f32_map(g_encode, &mY, Y, M, N, ldz, TM)) return 1; }
+    else mY = mZ;
+    GemmTcArgs g{(M + TM - 1) / TM, (N + TN - 1) / TN, (K + 31) / 32, 1, 0, 0, 0, 0, 0, Y != nullptr ? 2 : 1, N};
+    const int blocks = g.tiles_m * g.tiles_n;
+    gemm_tc_kernel<0><<<blocks < g_sms ? blocks : g_sms, THREADS, smem_bytes<0>(), s>>>(mA, mB, mZ, mY, bias, g);
     CB2_LAUNCH_CHECK();
     return 0;
 }
@@ -305,9 +347,9 @@ int gemm_tc_tn(const float* A, const float* B, float* C, int P, int Q, int R, lo
     const int tn_layout = 1, tn_sbo = 512;
     if (encode_f32_map(g_encode, &mA, A, R, P, lda, 64, swz) || encode_f32_map(g_encode, &mB, B, R, Q, ldb, 64, swz) ||
         encode_f32_map(g_encode, &mC, out, splits > 1 ? (long long)splits * P : P, Q, ld_out, TM)) return 1;
-    GemmTcArgs g{P / TM, Q / TN, rows_per_split / 64, splits, rows_per_split, splits > 1 ? 0 : accumulate, P, tn_sbo, tn_layout};
+    GemmTcArgs g{P / TM, Q / TN, rows_per_split / 64, splits, rows_per_split, splits > 1 ? 0 : accumulate, P, tn_sbo, tn_layout, 0, Q};
     const int blocks = tiles * splits;
-    gemm_tc_kernel<1><<<blocks < g_sms ? blocks : g_sms, THREADS, smem_bytes<1>(), s>>>(mA, mB, mC, g);
+    gemm_tc_kernel<1><<<blocks < g_sms ? blocks : g_sms, THREADS, smem_bytes<1>(), s>>>(mA, mB, mC, mC, nullptr, g);
     CB2_LAUNCH_CHECK();
     if (splits > 1) {
         const long long MN = (long long)P * Q;

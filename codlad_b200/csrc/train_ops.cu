@@ -64,6 +64,22 @@ __global__ void elementwise_kernel(int mode, const float* __restrict__ a, const 
     else out[i] = x * b[i];
 }
 
+__device__ __forceinline__ float ew_op(int mode, float x, float y, float scale) {
+    if (mode == 0) return silu(x);
+    if (mode == 1) { const float sg = 1.0f / (1.0f + expf(-x)); return y * (sg * (1.0f + x * (1.0f - sg))); }
+    if (mode == 2) return x + y;
+    if (mode == 3) return x * scale;
+    return x * y;
+}
+__global__ void elementwise_vec_kernel(int mode, const float* __restrict__ a, const float* __restrict__ b, float scale, long long n4, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == 1 || mode == 2 || mode == 4) y = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(ew_op(mode, x.x, y.x, scale), ew_op(mode, x.y, y.y, scale), ew_op(mode, x.z, y.z, scale), ew_op(mode, x.w, y.w, scale));
+}
+
 // one warp per edge row
 __global__ void __launch_bounds__(256) edge_combine_gelu_kernel(float* __restrict__ Z, const float* __restrict__ Pa, const float* __restrict__ Pc,
                                                                 const float* __restrict__ bias, const int* __restrict__ nbr_node, int K,
@@ -309,12 +325,62 @@ __global__ void __launch_bounds__(256) colsum_part_vec_kernel(const float* __res
         *reinterpret_cast<float4*>(part + (long long)blockIdx.x * cols + threadIdx.x * 4) = t;
     }
 }
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, int n_part, int cols, float* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// dpre = dY * GELU'(pre) and the column sums of dpre (the bias gradient of the layer that produced `pre`) in the same pass: the layout of
+// colsum_part_vec_kernel (thread = one float4 column group of one row lane), so the sums come out in the same fixed order.
+__global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const float* __restrict__ pre, const float* __restrict__ dY, long long rows, int cols,
+                                                              int rows_per_cta, float* __restrict__ dpre, float* __restrict__ part) {
+    __shared__ float4 red[256];
+    const int groups = cols >> 2, lanes = 256 / groups;
+    const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes) {
+        // four rows in flight per thread (eight 16-byte loads): the sums are still added in row order
+        constexpr int U = 4;
+        for (long long r = r0 + lane; r < r1; r += (long long)U * lanes) {
+            float4 z[U], g[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long ru = r + (long long)u * lanes;
+                if (ru < r1) {
+                    z[u] = *reinterpret_cast<const float4*>(pre + ru * cols + cg * 4);
+                    g[u] = *reinterpret_cast<const float4*>(dY + ru * cols + cg * 4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long ru = r + (long long)u * lanes;
+                if (ru < r1) {
+                    const float4 d = make_float4(g[u].x * gelu_grad(z[u].x), g[u].y * gelu_grad(z[u].y), g[u].z * gelu_grad(z[u].z), g[u].w * gelu_grad(z[u].w));
+                    *reinterpret_cast<float4*>(dpre + ru * cols + cg * 4) = d;
+                    s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+                }
+            }
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { const float4 v = red[l * groups + threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }      // fixed order
+        *reinterpret_cast<float4*>(part + (long long)blockIdx.x * cols + threadIdx.x * 4) = t;
+    }
+}
+// second pass of the column sums: block = 32 columns x 8 partial lanes; lane l adds partials l, l + 8, ... in order, the 8 lane sums are then
+// added in lane order (fixed order, deterministic)
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int n_part, int cols, float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][32];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), l = threadIdx.x >> 5;
     float s = 0.f;
-    for (int q = 0; q < n_part; ++q) s += part[(long long)q * cols + c];
-    out[c] = accumulate ? out[c] + s : s;
+    if (c < cols)
+        for (int q = l; q < n_part; q += 8) s += part[(long long)q * cols + c];
+    red[l][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (l == 0 && c < cols) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        out[c] = accumulate ? out[c] + t : t;
+    }
 }
 
 __global__ void __launch_bounds__(256) sumsq_part_kernel(const float* __restrict__ x, long long n, float* __restrict__ part) {
@@ -407,6 +473,19 @@ int cb2t_bias_gelu_fwd(float* Z, const float* bias, long long rows, int cols, fl
     return 0;
 }
 
+int cb2t_linear_bias_gelu_fwd(const float* X, const float* W, const float* bias, float* Z, float* Y, int M, int N, int K, long long ldx, long long ldw,
+                              long long ldz, void* stream) {
+    if (!X || !W || !bias || !Z) { set_error("cb2t_linear_bias_gelu_fwd: null argument"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    // tensor-core mode: bias and GELU ride in the GEMM's epilogue (Z and Y leave the kernel together)
+    if (g_gemm_mode == 1 && N % 32 == 0 && reinterpret_cast<uintptr_t>(bias) % 16 == 0 && (Y == nullptr || reinterpret_cast<uintptr_t>(Y) % 16 == 0) &&
+        tc_shape_ok(X, W, Z, M, N, K, ldx, ldw, ldz, 1, 1))
+        return gemm_tc_nt_bias_gelu(X, W, bias, Z, Y, M, N, K, ldx, ldw, ldz, s);
+    if (ldz != N) { set_error("cb2t_linear_bias_gelu_fwd: the unfused path needs contiguous Z"); return 1; }
+    if (int e = gemm(X, W, Z, M, N, K, ldx, ldw, ldz, 1, 1, 0, s)) return e;
+    return cb2t_bias_gelu_fwd(Z, bias, M, N, Y, stream);
+}
+
 int cb2t_gelu_bwd(const float* pre, const float* dY, long long n, float* dpre, void* stream) {
     if (!pre || !dY || !dpre || n % 4 != 0) { set_error("cb2t_gelu_bwd: bad argument"); return 1; }
     gelu_bwd_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, dY, n, dpre);
@@ -416,6 +495,12 @@ int cb2t_gelu_bwd(const float* pre, const float* dY, long long n, float* dpre, v
 
 int cb2t_elementwise(int mode, const float* a, const float* b, float scale, long long n, float* out, void* stream) {
     if (!a || !out || mode < 0 || mode > 4 || ((mode == 1 || mode == 2 || mode == 4) && !b)) { set_error("cb2t_elementwise: bad argument"); return 1; }
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(b);
+    if (n % 4 == 0 && al % 16 == 0) {
+        elementwise_vec_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mode, a, b, scale, n / 4, out);
+        CB2_LAUNCH_CHECK();
+        return 0;
+    }
     elementwise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mode, a, b, scale, n, out);
     CB2_LAUNCH_CHECK();
     return 0;
@@ -514,7 +599,21 @@ int cb2t_colsum(const float* X, long long rows, int cols, long long ld, float* o
     if (vec) colsum_part_vec_kernel<<<n_part, 256, 0, (cudaStream_t)stream>>>(X, rows, cols, ld, rows_per_cta, part);
     else colsum_part_kernel<<<n_part, 256, 0, (cudaStream_t)stream>>>(X, rows, cols, ld, rows_per_cta, part);
     CB2_LAUNCH_CHECK();
-    colsum_reduce_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, n_part, cols, out, accumulate);
+    colsum_reduce_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part, n_part, cols, out, accumulate);
+    CB2_LAUNCH_CHECK();
+    return 0;
+}
+
+int cb2t_gelu_bwd_colsum(const float* pre, const float* dY, long long rows, int cols, float* dpre, float* colsum_out, int accumulate, void* stream) {
+    if (!pre || !dY || !dpre || !colsum_out) { set_error("cb2t_gelu_bwd_colsum: null argument"); return 1; }
+    if (cols % 4 != 0 || cols > 1024 || 256 % (cols / 4) != 0) { set_error("cb2t_gelu_bwd_colsum: cols=%d unsupported", cols); return 1; }
+    const int n_part = (int)(rows < 1184 * 32 ? (rows + 31) / 32 : 1184);
+    const int rows_per_cta = (int)((rows + n_part - 1) / n_part);
+    float* part = nullptr;
+    if (int e = workspace((size_t)n_part * cols * sizeof(float), &part)) return e;
+    gelu_bwd_colsum_kernel<<<n_part, 256, 0, (cudaStream_t)stream>>>(pre, dY, rows, cols, rows_per_cta, dpre, part);
+    CB2_LAUNCH_CHECK();
+    colsum_reduce_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part, n_part, cols, colsum_out, accumulate);
     CB2_LAUNCH_CHECK();
     return 0;
 }

@@ -74,13 +74,26 @@ class _Ops:
     def colsum(self, X, out, acc=True):
         N.check(self.lib.cb2t_colsum(_p(X), X.shape[0], X.shape[1], X.stride(0), _p(out), int(acc), N.stream_ptr()), "colsum")
 
+    def linear_bias_act(self, x, W, bias, c0, kin, want_act=True):
+        """(Z, Y) = (x @ W[:, c0:c0+kin]^T + bias, GELU(Z) or None): one fused kernel in TF32 mode (cb2t_linear_bias_gelu_fwd)."""
+        M, nout, ldw = x.shape[0], W.shape[0], W.shape[1]
+        Z = torch.empty(M, nout, device=x.device, dtype=torch.float32)
+        Y = torch.empty_like(Z) if want_act else None
+        N.check(self.lib.cb2t_linear_bias_gelu_fwd(x.data_ptr(), W.data_ptr() + 4 * c0, _p(bias), _p(Z), _p(Y), M, nout, kin, x.stride(0), ldw, nout,
+                                                   N.stream_ptr()), "linear_bias_gelu_fwd")
+        return Z, Y
+
     def bias_gelu(self, Z, bias, want_act=True):
         Y = torch.empty_like(Z) if want_act else None
         N.check(self.lib.cb2t_bias_gelu_fwd(_p(Z), _p(bias), Z.shape[0], Z.shape[1], _p(Y), N.stream_ptr()), "bias_gelu_fwd")
         return Y
 
-    def gelu_bwd(self, pre, dY):
-        N.check(self.lib.cb2t_gelu_bwd(_p(pre), _p(dY), pre.numel(), _p(dY), N.stream_ptr()), "gelu_bwd")
+    def gelu_bwd(self, pre, dY, bias_grad=None):
+        """dY <- dY * GELU'(pre) in place; bias_grad (+)= its column sums in the same pass (the bias gradient of the layer behind `pre`)."""
+        if bias_grad is not None:
+            N.check(self.lib.cb2t_gelu_bwd_colsum(_p(pre), _p(dY), pre.shape[0], pre.shape[1], _p(dY), _p(bias_grad), 1, N.stream_ptr()), "gelu_bwd_colsum")
+        else:
+            N.check(self.lib.cb2t_gelu_bwd(_p(pre), _p(dY), pre.numel(), _p(dY), N.stream_ptr()), "gelu_bwd")
         return dY
 
     def ew(self, mode, a, b=None, scale=1.0, out=None):
@@ -247,19 +260,15 @@ class DenoiserTrainer:
     def _mlp_tail(self, A1, p, names, ctx, tag):
         """W2 -> GELU -> W3 (+ bias); keeps what the backward needs."""
         o, P = self.ops, self.params
-        Z2 = o.linear(A1, P[f"{p}.{names[1]}.weight"], 0, H)
-        A2 = o.bias_gelu(Z2, P[f"{p}.{names[1]}.bias"])
-        M = o.linear(A2, P[f"{p}.{names[2]}.weight"], 0, H)
-        o.bias_gelu(M, P[f"{p}.{names[2]}.bias"], want_act=False)
+        Z2, A2 = o.linear_bias_act(A1, P[f"{p}.{names[1]}.weight"], P[f"{p}.{names[1]}.bias"], 0, H)
+        M, _ = o.linear_bias_act(A2, P[f"{p}.{names[2]}.weight"], P[f"{p}.{names[2]}.bias"], 0, H, want_act=False)
         ctx[tag] = (A1, Z2, A2)
         return M
 
     def _ffn(self, h, p, ctx):
         o, P = self.ops, self.params
-        F1 = o.linear(h, P[f"{p}.dense.W_in.weight"], 0, H)
-        G1 = o.bias_gelu(F1, P[f"{p}.dense.W_in.bias"])
-        F2 = o.linear(G1, P[f"{p}.dense.W_out.weight"], 0, 4 * H)
-        o.bias_gelu(F2, P[f"{p}.dense.W_out.bias"], want_act=False)
+        F1, G1 = o.linear_bias_act(h, P[f"{p}.dense.W_in.weight"], P[f"{p}.dense.W_in.bias"], 0, H)
+        F2, _ = o.linear_bias_act(G1, P[f"{p}.dense.W_out.weight"], P[f"{p}.dense.W_out.bias"], 0, 4 * H, want_act=False)
         ctx[p + ".ffn"] = (h, F1, G1)
         return F2
 
@@ -334,8 +343,7 @@ class DenoiserTrainer:
         lnw, lnb = P["features.norm_edges.weight"], P["features.norm_edges.bias"]
         lnw1 = (lnw - 1.0).contiguous()
         Efeat, _, stE = o.ln_mod(Epre, None, None, g.E, lnb.data_ptr(), lnw1.data_ptr(), None, 0, None, eps=1e-5)
-        hE = o.linear(Efeat, P["W_e.weight"], 0, H)
-        o.bias_gelu(hE, P["W_e.bias"], want_act=False)
+        hE, _ = o.linear_bias_act(Efeat, P["W_e.weight"], P["W_e.bias"], 0, H, want_act=False)
         ctx["feat"] = (posT, Epre, stE, Efeat, lnw1)
         return hE
 
@@ -394,14 +402,14 @@ class DenoiserTrainer:
         """Backward of W3(GELU(W2 A1 + b2)) + b3 -> dA1."""
         A1, Z2, A2 = self.ctx[tag]
         dA2 = self._lin_bwd(dM, A2, f"{p}.{names[2]}", 0, H)
-        dZ2 = self.ops.gelu_bwd(Z2, dA2)
-        return self._lin_bwd(dZ2, A1, f"{p}.{names[1]}", 0, H)
+        dZ2 = self.ops.gelu_bwd(Z2, dA2, bias_grad=self.grads[f"{p}.{names[1]}.bias"])
+        return self._lin_bwd(dZ2, A1, f"{p}.{names[1]}", 0, H, bias=False)
 
     def _ffn_bwd(self, dF2, p, dh_acc):
         h, F1, G1 = self.ctx[p + ".ffn"]
         dG1 = self._lin_bwd(dF2, G1, p + ".dense.W_out", 0, 4 * H)
-        dF1 = self.ops.gelu_bwd(F1, dG1)
-        self._lin_bwd(dF1, h, p + ".dense.W_in", 0, H, dx_out=dh_acc, dx_acc=True)
+        dF1 = self.ops.gelu_bwd(F1, dG1, bias_grad=self.grads[p + ".dense.W_in.bias"])
+        self._lin_bwd(dF1, h, p + ".dense.W_in", 0, H, dx_out=dh_acc, dx_acc=True, bias=False)
 
     def _adaln_bwd(self, name, dmod, d_c_silu):
         c_silu = self.ctx["temb"][4]
@@ -423,8 +431,7 @@ class DenoiserTrainer:
         dhE = dX3                                                                          # residual branch (aliased on purpose, read-only from here)
         dM3 = self._mul(dX3, s["d3"])
         dA11 = self._mlp_tail_bwd(dM3, p, ("W11", "W12", "W13"), p + ".upd")
-        dZ11 = o.gelu_bwd(s["Z11"], dA11)
-        o.colsum(dZ11, G[p + ".W11.bias"])
+        dZ11 = o.gelu_bwd(s["Z11"], dA11, bias_grad=G[p + ".W11.bias"])
         W11 = P[p + ".W11.weight"]
         o.linear_dw(dZ11, s["hE"], G[p + ".W11.weight"], H)
         dhE_total = o.linear_dx(dZ11, W11, H, H)
@@ -443,8 +450,7 @@ class DenoiserTrainer:
         dhV = dX1.clone()
         dM = o.masked_sum_bwd(self._mul(dX1, s["d1"]), g.mask_e, g)
         dA1 = self._mlp_tail_bwd(dM, p, ("W1", "W2", "W3"), p + ".msg")
-        dZ1 = o.gelu_bwd(s["Z1"], dA1)
-        o.colsum(dZ1, G[p + ".W1.bias"])
+        dZ1 = o.gelu_bwd(s["Z1"], dA1, bias_grad=G[p + ".W1.bias"])
         W1 = P[p + ".W1.weight"]
         o.linear_dw(dZ1, s["hE"], G[p + ".W1.weight"], H)
         o.linear_dx(dZ1, W1, H, H, out=dhE_total, acc=True)
@@ -472,8 +478,7 @@ class DenoiserTrainer:
         dhV = dX1.clone()
         dM = o.masked_sum_bwd(self._mul(dX1, s["d1"]), None, g)
         dA1 = self._mlp_tail_bwd(dM, p, ("W1", "W2", "W3"), p + ".msg")
-        dZ1 = o.gelu_bwd(s["Z1"], dA1)
-        o.colsum(dZ1, G[p + ".W1.bias"])
+        dZ1 = o.gelu_bwd(s["Z1"], dA1, bias_grad=G[p + ".W1.bias"])
         W1 = P[p + ".W1.weight"]
         o.linear_dw(dZ1, hE2x, G[p + ".W1.weight"], H)
         o.linear_dx(dZ1, W1, H, H, out=dhE2x, acc=True)

@@ -34,8 +34,17 @@ CB2_API int cb2t_set_gemm_mode(int mode);
 /* Replaces: `+ bias` and torch.nn.GELU() (exact erf form; protein_mpnn_utils.py:227,243,325).  Z [rows, cols] <- Z + bias (kept as the
  * pre-activation), Y <- GELU(Z) when Y != NULL.  bias may be NULL. */
 CB2_API int cb2t_bias_gelu_fwd(float* Z, const float* bias, long long rows, int cols, float* Y, void* stream);
+/* Replaces: torch.nn.Linear followed by torch.nn.GELU() in one call (the W2 / W3 / W12 / W13 / dense layers, protein_mpnn_utils.py:240-247,
+ * 261-270, 300-307, 319-330).  Z [M, N] = X [M, K] W [N, K]^T + bias (kept: the backward needs the pre-activation), Y = GELU(Z) when Y != NULL
+ * (same pitch ldz as Z).  In TF32 mode the bias and the GELU run in the GEMM's epilogue; otherwise it is cb2t_gemm + cb2t_bias_gelu_fwd. */
+CB2_API int cb2t_linear_bias_gelu_fwd(const float* X, const float* W, const float* bias, float* Z, float* Y, int M, int N, int K, long long ldx,
+                              long long ldw, long long ldz, void* stream);
 /* dpre = dY * GELU'(pre) (autograd of the above; in place allowed). */
 CB2_API int cb2t_gelu_bwd(const float* pre, const float* dY, long long n, float* dpre, void* stream);
+/* The same with the bias gradient of the layer that produced `pre` in the same pass: colsum_out [cols] (+)= column sums of dpre
+ * (autograd's `.sum(0)` for a Linear bias; two passes, fixed order).  pre, dY, dpre [rows, cols] contiguous, cols % 4 == 0. */
+CB2_API int cb2t_gelu_bwd_colsum(const float* pre, const float* dY, long long rows, int cols, float* dpre, float* colsum_out, int accumulate,
+                         void* stream);
 
 /* mode 0: out = SiLU(a) (adaLN_modulation.0, t_embedder.mlp.1); 1: out = b * SiLU'(a); 2: out = a + b; 3: out = a * scale; 4: out = a * b (dropout masks). */
 CB2_API int cb2t_elementwise(int mode, const float* a, const float* b, float scale, long long n, float* out, void* stream);

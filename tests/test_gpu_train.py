@@ -75,6 +75,54 @@ def test_gemm_tf32_tensor_cores_against_float64(M, N, K, a_kc, b_kc):
         Nn.check(Nn.lib().cb2t_set_gemm_mode(0))
 
 
+@pytest.mark.parametrize("mode,M,N,K,act", [(1, 4096, 128, 128, True), (1, 5001, 512, 128, True), (1, 3000, 128, 512, False), (1, 2048, 64, 96, True),
+                                            (0, 700, 128, 128, True), (0, 300, 128, 128, False), (1, 500, 128, 128, True)])
+def test_fused_linear_bias_gelu_against_float64(mode, M, N, K, act):
+    """cb2t_linear_bias_gelu_fwd: Z = X W^T + b and Y = GELU(Z).  In TF32 mode (large M) bias and GELU run in the tensor-core GEMM's epilogue
+    (two stores per accumulator block, M tails clipped by the TMA stores); small M or fp32 mode take the GEMM + elementwise pair.  Both outputs
+    against float64; Y must be GELU of the Z that was stored (bit-for-bit the same erf formula)."""
+    from codlad_b200 import _native as Nn
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    X, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    Zref = X.double() @ W.double().t() + b.double()
+    Xd, Wd, bd = X.cuda(), W.cuda(), b.cuda()
+    Z = torch.full((M, N), float("nan"), device="cuda")
+    Y = torch.full((M, N), float("nan"), device="cuda") if act else None
+    try:
+        Nn.check(Nn.lib().cb2t_set_gemm_mode(mode))
+        Nn.check(Nn.lib().cb2t_linear_bias_gelu_fwd(Xd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), Z.data_ptr(), Y.data_ptr() if act else None, M, N, K, K, K, N,
+                                                    Nn.stream_ptr()))
+    finally:
+        Nn.check(Nn.lib().cb2t_set_gemm_mode(0))
+    bar = 2e-3 if mode == 1 and M >= 1024 else 3e-6
+    err = float((Z.cpu().double() - Zref).abs().max() / Zref.abs().max())
+    assert err < bar, err
+    if mode == 1 and M >= 1024:
+        assert err > 1e-5                                    # the tensor-core path really ran
+    if act:
+        want = torch.nn.functional.gelu(Z.cpu().double())
+        assert float((Y.cpu().double() - want).abs().max()) < 2e-6
+
+
+def test_gelu_backward_with_bias_gradient():
+    """cb2t_gelu_bwd_colsum = cb2t_gelu_bwd followed by cb2t_colsum, in one pass: identical dZ, bias gradient equal to the separate column sum
+    (same partition and order: bit-identical) and to float64 within fp32 summation error; accumulates into the gradient."""
+    from codlad_b200 import _native as Nn
+    g = torch.Generator().manual_seed(77)
+    for rows, cols in ((50000, 128), (3001, 512), (17, 128)):
+        pre, dY = torch.randn(rows, cols, generator=g).cuda(), torch.randn(rows, cols, generator=g).cuda()
+        d1, d2 = dY.clone(), dY.clone()
+        b0 = torch.randn(cols, generator=g).cuda()
+        b1, b2 = b0.clone(), b0.clone()
+        lib = Nn.lib()
+        Nn.check(lib.cb2t_gelu_bwd(pre.data_ptr(), d1.data_ptr(), rows * cols, d1.data_ptr(), Nn.stream_ptr()))
+        Nn.check(lib.cb2t_colsum(d1.data_ptr(), rows, cols, cols, b1.data_ptr(), 1, Nn.stream_ptr()))
+        Nn.check(lib.cb2t_gelu_bwd_colsum(pre.data_ptr(), d2.data_ptr(), rows, cols, d2.data_ptr(), b2.data_ptr(), 1, Nn.stream_ptr()))
+        assert torch.equal(d1, d2) and torch.equal(b1, b2)
+        want = b0.double().cpu() + d1.double().cpu().sum(0)
+        assert float((b2.cpu().double() - want).abs().max()) < 1e-4 * max(1.0, float(want.abs().max()))
+
+
 def test_denoiser_gradients_tf32_mode(R):
     """The same backward with the large GEMMs on the tensor cores in TF32 -- the arithmetic the reference trains with (train_latent.py:24-25).
     Against fp32 autograd every gradient tensor stays within 1e-2 of its norm (measured ~2e-3), the model output within 5e-3."""

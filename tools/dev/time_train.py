@@ -6,13 +6,13 @@ from codlad_b200 import synthetic, train, weights
 from codlad_b200.diffusion import create_diffusion
 mode = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 rnd = random.Random(5000)
-lens = sorted([rnd.randint(60, 400) for _ in range(128)], reverse=True)[:16]
+lens = sorted([rnd.randint(60, 400) for _ in range(128)], reverse=True)[:64]
 prots = [synthetic.make_protein(n, 1, seed=5100 + i) for i, n in enumerate(lens)]
 batch = synthetic.collate_many(prots)
 tr = train.DenoiserTrainer(weights.init_denoiser_state(0), gemm=mode)
 diffusion = create_diffusion("")
-x1 = torch.randn(16, max(lens), 3)
-t = torch.randint(0, 1000, (16,))
+x1 = torch.randn(64, max(lens), 3)
+t = torch.randint(0, 1000, (64,))
 def timed(fn, n=3):
     fn(); torch.cuda.synchronize()
     t0 = time.perf_counter()
