@@ -333,9 +333,10 @@ def run_train(args):
     losses = []
     for a, b in ev:
         a.record()
-        losses.append(one_step())
+        losses.append(one_step())                       # device scalars: nothing inside a step waits for the GPU
         b.record()
     D.barrier()
+    losses = [float(v) for v in losses]
     ms = D.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / args.steps, dev)
     residues = sum(lens)
     padded = D.gather_counts(sum(max(lens[i] for i in g) * len(g) for g in groups), dev)

@@ -43,9 +43,10 @@ class _Ops:
     def __init__(self):
         self.lib = N.lib()
         self.transposed = {}           # data_ptr of a weight view -> its transposed copy (TF32 mode only)
+        self.stream = N.stream_ptr()   # refreshed on entry of forward / backward (a pass makes ~1 500 calls)
 
     def gemm(self, A, B, Cm, M, Nn, K, lda, ldb, ldc, a_kc, b_kc, acc=False):
-        N.check(self.lib.cb2t_gemm(A, B, Cm, int(M), int(Nn), int(K), int(lda), int(ldb), int(ldc), int(a_kc), int(b_kc), int(acc), N.stream_ptr()),
+        N.check(self.lib.cb2t_gemm(A, B, Cm, int(M), int(Nn), int(K), int(lda), int(ldb), int(ldc), int(a_kc), int(b_kc), int(acc), self.stream),
                 "gemm")
 
     # y[M, out] = x[M, in] @ W[out, in_total][:, c0:c0+in]^T   (W given as (tensor, col0, in))
@@ -72,7 +73,7 @@ class _Ops:
         self.gemm(dy.data_ptr(), x.data_ptr(), dW.data_ptr() + 4 * c0, nout, kin, M, dy.stride(0), x.stride(0), dW.shape[1], 0, 0, True)
 
     def colsum(self, X, out, acc=True):
-        N.check(self.lib.cb2t_colsum(_p(X), X.shape[0], X.shape[1], X.stride(0), _p(out), int(acc), N.stream_ptr()), "colsum")
+        N.check(self.lib.cb2t_colsum(_p(X), X.shape[0], X.shape[1], X.stride(0), _p(out), int(acc), self.stream), "colsum")
 
     def linear_bias_act(self, x, W, bias, c0, kin, want_act=True):
         """(Z, Y) = (x @ W[:, c0:c0+kin]^T + bias, GELU(Z) or None): one fused kernel in TF32 mode (cb2t_linear_bias_gelu_fwd)."""
@@ -80,46 +81,46 @@ class _Ops:
         Z = torch.empty(M, nout, device=x.device, dtype=torch.float32)
         Y = torch.empty_like(Z) if want_act else None
         N.check(self.lib.cb2t_linear_bias_gelu_fwd(x.data_ptr(), W.data_ptr() + 4 * c0, _p(bias), _p(Z), _p(Y), M, nout, kin, x.stride(0), ldw, nout,
-                                                   N.stream_ptr()), "linear_bias_gelu_fwd")
+                                                   self.stream), "linear_bias_gelu_fwd")
         return Z, Y
 
     def bias_gelu(self, Z, bias, want_act=True):
         Y = torch.empty_like(Z) if want_act else None
-        N.check(self.lib.cb2t_bias_gelu_fwd(_p(Z), _p(bias), Z.shape[0], Z.shape[1], _p(Y), N.stream_ptr()), "bias_gelu_fwd")
+        N.check(self.lib.cb2t_bias_gelu_fwd(_p(Z), _p(bias), Z.shape[0], Z.shape[1], _p(Y), self.stream), "bias_gelu_fwd")
         return Y
 
     def gelu_bwd(self, pre, dY, bias_grad=None):
         """dY <- dY * GELU'(pre) in place; bias_grad (+)= its column sums in the same pass (the bias gradient of the layer behind `pre`)."""
         if bias_grad is not None:
-            N.check(self.lib.cb2t_gelu_bwd_colsum(_p(pre), _p(dY), pre.shape[0], pre.shape[1], _p(dY), _p(bias_grad), 1, N.stream_ptr()), "gelu_bwd_colsum")
+            N.check(self.lib.cb2t_gelu_bwd_colsum(_p(pre), _p(dY), pre.shape[0], pre.shape[1], _p(dY), _p(bias_grad), 1, self.stream), "gelu_bwd_colsum")
         else:
-            N.check(self.lib.cb2t_gelu_bwd(_p(pre), _p(dY), pre.numel(), _p(dY), N.stream_ptr()), "gelu_bwd")
+            N.check(self.lib.cb2t_gelu_bwd(_p(pre), _p(dY), pre.numel(), _p(dY), self.stream), "gelu_bwd")
         return dY
 
     def ew(self, mode, a, b=None, scale=1.0, out=None):
         out = out if out is not None else torch.empty_like(a)
-        N.check(self.lib.cb2t_elementwise(mode, _p(a), _p(b), float(scale), a.numel(), _p(out), N.stream_ptr()), "elementwise")
+        N.check(self.lib.cb2t_elementwise(mode, _p(a), _p(b), float(scale), a.numel(), _p(out), self.stream), "elementwise")
         return out
 
     def edge_combine_gelu(self, Z, Pa, Pc, bias, g):
         Y = torch.empty_like(Z)
-        N.check(self.lib.cb2t_edge_combine_gelu_fwd(_p(Z), _p(Pa), _p(Pc), _p(bias), _p(g.nbr_node), g.K, Z.shape[0], _p(Y), N.stream_ptr()), "edge_combine")
+        N.check(self.lib.cb2t_edge_combine_gelu_fwd(_p(Z), _p(Pa), _p(Pc), _p(bias), _p(g.nbr_node), g.K, Z.shape[0], _p(Y), self.stream), "edge_combine")
         return Y
 
     def edge_gather_bwd(self, dZ, g):
         dPa = torch.empty(g.Nn, H, device=dZ.device)
         dPc = torch.empty(g.Nn, H, device=dZ.device)
-        N.check(self.lib.cb2t_edge_gather_bwd(_p(dZ), g.K, g.Nn, _p(g.rev_ptr), _p(g.rev_edge), _p(dPa), _p(dPc), N.stream_ptr()), "edge_gather_bwd")
+        N.check(self.lib.cb2t_edge_gather_bwd(_p(dZ), g.K, g.Nn, _p(g.rev_ptr), _p(g.rev_edge), _p(dPa), _p(dPc), self.stream), "edge_gather_bwd")
         return dPa, dPc
 
     def masked_sum(self, M, mask_e, g):
         S = torch.empty(g.Nn, H, device=M.device)
-        N.check(self.lib.cb2t_masked_sum_fwd(_p(M), _p(mask_e), g.K, g.Nn, 1.0 / 30.0, _p(S), N.stream_ptr()), "masked_sum_fwd")
+        N.check(self.lib.cb2t_masked_sum_fwd(_p(M), _p(mask_e), g.K, g.Nn, 1.0 / 30.0, _p(S), self.stream), "masked_sum_fwd")
         return S
 
     def masked_sum_bwd(self, dS, mask_e, g):
         dM = torch.empty(g.E, H, device=dS.device)
-        N.check(self.lib.cb2t_masked_sum_bwd(_p(dS), _p(mask_e), g.K, g.E, 1.0 / 30.0, _p(dM), N.stream_ptr()), "masked_sum_bwd")
+        N.check(self.lib.cb2t_masked_sum_bwd(_p(dS), _p(mask_e), g.K, g.E, 1.0 / 30.0, _p(dM), self.stream), "masked_sum_bwd")
         return dM
 
     def ln_mod(self, A, Bres, drop, rpm, shift, scale, gate, stride, row_mask, eps=1e-6):
@@ -128,17 +129,17 @@ class _Ops:
         stats = torch.empty(rows, 2, device=A.device)
         Y = torch.empty_like(A)
         N.check(self.lib.cb2t_ln_mod_fwd(_p(A), _p(Bres), _p(drop), rows, int(rpm), shift, scale, gate, int(stride), _p(row_mask), float(eps), _p(X),
-                                         _p(stats), _p(Y), N.stream_ptr()), "ln_mod_fwd")
+                                         _p(stats), _p(Y), self.stream), "ln_mod_fwd")
         return Y, (X if X is not None else A), stats
 
     def ln_mod_bwd(self, dY, X, stats, rpm, shift, scale, gate, stride, row_mask, d_shift, d_scale, d_gate, acc=False):
         dX = torch.empty_like(X)
         N.check(self.lib.cb2t_ln_mod_bwd(_p(dY), _p(X), _p(stats), X.shape[0], int(rpm), shift, scale, gate, int(stride), _p(row_mask), _p(dX),
-                                         d_shift, d_scale, d_gate, int(acc), N.stream_ptr()), "ln_mod_bwd")
+                                         d_shift, d_scale, d_gate, int(acc), self.stream), "ln_mod_bwd")
         return dX
 
     def index_sum(self, X, idx, classes, out, acc=True):
-        N.check(self.lib.cb2t_index_sum(_p(X), _p(idx), X.shape[0], X.shape[1], int(classes), _p(out), int(acc), N.stream_ptr()), "index_sum")
+        N.check(self.lib.cb2t_index_sum(_p(X), _p(idx), X.shape[0], X.shape[1], int(classes), _p(out), int(acc), self.stream), "index_sum")
 
 
 def allreduce_flat(flat_g: torch.Tensor, n_buckets: int = 4):
@@ -244,6 +245,8 @@ class DenoiserTrainer:
         """The GEMM arithmetic is a switch of the library (cb2t_set_gemm_mode), read when a GEMM is launched: set on entry of forward /
         backward, back to the fp32 default on exit so that nothing else in the process inherits TF32."""
         N.check(self.ops.lib.cb2t_set_gemm_mode(1 if (on and self.gemm_mode == "tf32") else 0), "set_gemm_mode")
+        if on:
+            self.ops.stream = N.stream_ptr()
 
     def state_dict(self, ema: bool = False):
         src = self.ema if ema else self.params
@@ -592,4 +595,4 @@ class DenoiserTrainer:
             self.allreduce_grads()
         if do_step:
             self.step()
-        return {k: v.detach() for k, v in terms.items()}, float(loss.detach())
+        return {k: v.detach() for k, v in terms.items()}, loss.detach()          # 0-d device tensor: no host synchronisation inside a step

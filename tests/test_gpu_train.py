@@ -248,13 +248,14 @@ def test_train_step_loss_and_descent(R):
         ref = diffusion.training_losses(ref_model, x1, t, dict(mask=mask), noise=noise)
     for k in ("mse", "vb", "loss"):
         assert torch.allclose(terms[k].cpu(), ref[k], rtol=1e-3, atol=1e-5), (k, terms[k], ref[k])
-    losses = [loss0]
+    assert torch.is_tensor(loss0) and loss0.is_cuda and loss0.dim() == 0        # a device scalar like the reference's `loss`: no sync in the step
+    losses = [float(loss0)]
     for _ in range(12):
         _, l = tr.train_step(diffusion, x1, t, batch, noise=noise, geom=geom)
-        losses.append(l)
+        losses.append(float(l))
     print("losses", [round(v, 4) for v in losses])
     assert losses[-1] < 0.8 * losses[0]
     assert not torch.equal(tr.flat_ema, tr.flat_p) and float((tr.flat_ema - tr.flat_p).abs().max()) > 0
     # dropout path (the reference's p = 0.6) runs and stays finite
     _, ld = tr.train_step(diffusion, x1, t, batch, noise=noise, geom=geom, dropout_p=0.6, generator=torch.Generator(device="cuda").manual_seed(1))
-    assert np.isfinite(ld) and torch.isfinite(tr.flat_p).all()
+    assert np.isfinite(float(ld)) and torch.isfinite(tr.flat_p).all()
