@@ -70,12 +70,19 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
-constexpr int EPI_THREADS = 512;                // thread (row r, column quarter cq)
+#ifndef CB2_EPI_SUBS
+#define CB2_EPI_SUBS 1
+#endif
+// SUBS 32-column blocks per epilogue thread: 1 = sixteen warps, thread (row, column quarter); 2 = eight warps, thread (row, column half), each
+// stage instance walks its two blocks in turn (experiment builds: fewer, fatter warps with 168 registers)
+constexpr int SUBS = CB2_EPI_SUBS;
+constexpr int NCG = 4 / SUBS;                   // column groups (warps per TMEM lane quarter)
+constexpr int EPI_THREADS = 128 * NCG;          // thread (row r, column group cq)
 constexpr int CTA_THREADS = EPI_THREADS + 64;   // + two control warps (one lane each): MMA issue, TMA issue
 constexpr int NSLOT = 4;                        // tiles in flight per CTA (32 KB operand buffer + 128 TMEM columns each)
 
 // the four warps that hold the column quarters of the same 32 rows (row quarter q): named barrier 1 + q, 128 threads
-__device__ __forceinline__ void row_quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
+__device__ __forceinline__ void row_quarter_sync(int q) { asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(32 * NCG) : "memory"); }
 
 // per-thread view of a tile, packed into two registers (four of them are live; they rotate so that the stage code
 // exists once):  a = member << 16 | tile-within-member (advanced without divisions) ;  b = member-local neighbour index j
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
     } else {
         // =========================================================================== epilogue threads
         const int warp = tid >> 5, quarter = warp & 3, cq = warp >> 2, r = quarter * 32 + (tid & 31);
-        const int c0 = cq * 32;                                        // this thread's 32 accumulator columns
+        const int c0 = cq * 32 * SUBS;                                 // this thread's first accumulator column (32 SUBS columns in all)
         const int q_of_r = r / K;
         const int len0 = __ldg(p.lengths);                             // length of frame 0 (the only frame of an ensemble plan)
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
@@ -392,19 +399,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             const int len = p.single_frame ? len0 : __ldg(p.lengths + __ldg(p.frame_of + meta_member(m)));
             return (meta_tin(m) * NPT + q_of_r < len && meta_j(m) < len) ? 0xffffffffu : 0u;
         };
-        auto ld_pc = [&](const TileMeta& m, uint32_t (&pc)[16]) {       // this thread's 32 gathered halves of Pc[j]
+        auto ld_pc = [&](const TileMeta& m, int col, uint32_t (&pc)[16]) {       // 32 gathered halves of Pc[j] starting at column col
 #ifdef CB2_X_NOGATHER
-            const __half* src = p.P16 + 128 + c0;
+            const __half* src = p.P16 + 128 + col;
 #else
-            const __half* src = p.P16 + ((size_t)meta_member(m) * p.L + meta_j(m)) * 256 + 128 + c0;
+            const __half* src = p.P16 + ((size_t)meta_member(m) * p.L + meta_j(m)) * 256 + 128 + col;
 #endif
             ldg256(src, *reinterpret_cast<uint32_t(*)[8]>(&pc[0]));
             ldg256(src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pc[8]));
         };
         // packed-half store of 16 consecutive columns [c0 + g16*16, +16) of row r
-        auto st16 = [&](unsigned char* T, int g16, const uint32_t (&o)[8]) {
-            *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+        auto st16 = [&](unsigned char* T, int col, int g16, const uint32_t (&o)[8]) {
+            *reinterpret_cast<uint4*>(T + tile_off(r, (col >> 3) + g16 * 2)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(T + tile_off(r, (col >> 3) + g16 * 2 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         };
 
 #ifdef CB2_TRACE_EPI                                                    // epilogue timeline of CTA 0 / thread 0 (debug builds only: the marks
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
         auto drain = [&](int s, int next_tile) {
             const TileMeta m = m3;
             m3 = next_meta(m, next_tile);
-            if (cq == s) {                                               // slot s is drained by column group s (one warp per scheduler): the four
+            if (cq == s % NCG) {                                         // slot s is drained by column group s (one warp per scheduler): the four
                                                                          // groups share the drains, the other twelve warps run ahead
                 mark(8, s);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph ^ 1);           // third commit of the tile (reduction MMA)
@@ -458,46 +465,52 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
             // ================= E1: GELU(acc + Pa[i] + Pc[j]) -> fp16 activation tile
             auto epi1 = [&](int s) {
                 unsigned char* T = sT + s * TILE_BYTES;
-                uint32_t pc[16];                                        // gathered half of this tile's rows (loaded here, not a stage ahead:
-                ld_pc(m0, pc);                                          //  the registers a prefetch holds cost more than its latency)
-                uint32_t pa[16];                                        // own half: two nodes per tile, L1-resident after the first warp
-                const __half* pa_src = p.P16 + (size_t)(node0_of(m0) + (meta_row_valid(m0) ? q_of_r : 0)) * 256 + c0;
-                ldg256(pa_src, *reinterpret_cast<uint32_t(*)[8]>(&pa[0]));
-                ldg256(pa_src + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[8]));
+                uint32_t pc[SUBS][16];                                  // gathered half of this tile's rows (loaded here, not a stage ahead: measured slower,
+                uint32_t pa[SUBS][16];                                  //  with 96 and with 168 registers -- DESIGN.md section 4)
+                const __half* pa_src = p.P16 + (size_t)(node0_of(m0) + (meta_row_valid(m0) ? q_of_r : 0)) * 256 + c0;   // own half: two nodes per tile, L1-resident
+#pragma unroll
+                for (int sub = 0; sub < SUBS; ++sub) {
+                    ld_pc(m0, c0 + sub * 32, pc[sub]);
+                    ldg256(pa_src + sub * 32, *reinterpret_cast<uint32_t(*)[8]>(&pa[sub][0]));
+                    ldg256(pa_src + sub * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&pa[sub][8]));
+                }
                 mark(0, s);
                 // The warps that do not drain slot s (cq != s) never wait for the slot's third commit (the reduction MMA), and the phases
                 // on either side of it have the same parity: a warp that ran a whole E2 phase ahead of a straggler would sail
                 // through the accumulator wait below on the stale "MMA 2 complete" state (seen as a rare dead-lock on large
                 // working sets, where TLB misses skew the warps).  The slot's "drained" barrier advances once per round and
                 // only after the reduction has completed, so it orders them exactly.
-                if (MODE != EDGE_ENC_EDGE && cq != s && t0 != tile_begin) mbar_wait(smem_u32(&sBar[25 + s]), ph ^ 1);
+                if (MODE != EDGE_ENC_EDGE && cq != s % NCG && t0 != tile_begin) mbar_wait(smem_u32(&sBar[25 + s]), ph ^ 1);
                 mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                 tc_fence_after();
                 mark(1, s);
-                float acc0[16], acc1[16];
+#pragma unroll
+                for (int sub = 0; sub < SUBS; ++sub) {
+                    float acc0[16], acc1[16];
 #ifdef CB2_X_NOLDTM                                                     // timing ablations (tools/dev/build_variant.sh), never in the product build
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));
-                    asm volatile("mov.b32 %0, %1;" : "=f"(acc1[e]) : "r"(tid - e));
-                }
-#else
-                tmem_ld16x2(tmem_lane + (uint32_t)(s * 128), acc0, acc1);
-#endif
-#pragma unroll
-                for (int g16 = 0; g16 < 2; ++g16) {
-                    const float (&acc)[16] = g16 ? acc1 : acc0;
-                    uint32_t o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(pa[g16 * 8 + e])), as_h2(pc[g16 * 8 + e]));
-                        o[e] = as_u32(gelu2_h2(x));
+                    for (int e = 0; e < 16; ++e) {
+                        asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));
+                        asm volatile("mov.b32 %0, %1;" : "=f"(acc1[e]) : "r"(tid - e));
                     }
-#ifdef CB2_X_NOSTS
-                    if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, g16, o);
 #else
-                    st16(T, g16, o);
+                    tmem_ld16x2(tmem_lane + (uint32_t)(s * 128 + sub * 32), acc0, acc1);
 #endif
+#pragma unroll
+                    for (int g16 = 0; g16 < 2; ++g16) {
+                        const float (&acc)[16] = g16 ? acc1 : acc0;
+                        uint32_t o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const __half2 x = __hadd2(__hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(pa[sub][g16 * 8 + e])), as_h2(pc[sub][g16 * 8 + e]));
+                            o[e] = as_u32(gelu2_h2(x));
+                        }
+#ifdef CB2_X_NOSTS
+                        if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, c0 + sub * 32, g16, o);
+#else
+                        st16(T, c0 + sub * 32, g16, o);
+#endif
+                    }
                 }
                 mark(2, s);
                 stage_done(s, true);
@@ -519,41 +532,47 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                     // when the geometry has none of them (full-length frames, NPT K = 128) the whole step is skipped
                     constexpr bool masked = MODE != EDGE_ENC_EDGE && MASKED;
                     const uint32_t keep = masked ? row_keep(m0) : 0xffffffffu;
-                    uint32_t bb[16];
-                    ldg256(p.b2h + c0, *reinterpret_cast<uint32_t(*)[8]>(&bb[0]));
-                    ldg256(p.b2h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&bb[8]));
+                    uint32_t bb[SUBS][16];
+#pragma unroll
+                    for (int sub = 0; sub < SUBS; ++sub) {
+                        ldg256(p.b2h + c0 + sub * 32, *reinterpret_cast<uint32_t(*)[8]>(&bb[sub][0]));
+                        ldg256(p.b2h + c0 + sub * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&bb[sub][8]));
+                    }
                     mark(4, s);
                     mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                     tc_fence_after();
                     mark(5, s);
-                    float acc0[16], acc1[16];
+#pragma unroll
+                    for (int sub = 0; sub < SUBS; ++sub) {
+                        float acc0[16], acc1[16];
 #ifdef CB2_X_NOLDTM
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));
-                        asm volatile("mov.b32 %0, %1;" : "=f"(acc1[e]) : "r"(tid - e));
-                    }
+                        for (int e = 0; e < 16; ++e) {
+                            asm volatile("mov.b32 %0, %1;" : "=f"(acc0[e]) : "r"(tid + e));
+                            asm volatile("mov.b32 %0, %1;" : "=f"(acc1[e]) : "r"(tid - e));
+                        }
 #else
-                    tmem_ld16x2(tmem_lane + (uint32_t)(s * 128), acc0, acc1);
+                        tmem_ld16x2(tmem_lane + (uint32_t)(s * 128 + sub * 32), acc0, acc1);
 #endif
 #pragma unroll
-                    for (int g16 = 0; g16 < 2; ++g16) {
-                        const float (&acc)[16] = g16 ? acc1 : acc0;
-                        uint32_t o[8];
+                        for (int g16 = 0; g16 < 2; ++g16) {
+                            const float (&acc)[16] = g16 ? acc1 : acc0;
+                            uint32_t o[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const __half2 x = __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(bb[g16 * 8 + e]));
-                            o[e] = as_u32(gelu2_h2(x));
-                        }
-                        if (masked) {
+                            for (int e = 0; e < 8; ++e) {
+                                const __half2 x = __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(bb[sub][g16 * 8 + e]));
+                                o[e] = as_u32(gelu2_h2(x));
+                            }
+                            if (masked) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) o[e] &= keep;
-                        }
+                                for (int e = 0; e < 8; ++e) o[e] &= keep;
+                            }
 #ifdef CB2_X_NOSTS
-                        if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, g16, o);
+                            if (o[0] == 0x12345678u && o[5] == 0x9abcdef0u) st16(T, c0 + sub * 32, g16, o);
 #else
-                        st16(T, g16, o);
+                            st16(T, c0 + sub * 32, g16, o);
 #endif
+                        }
                     }
                     mark(6, s);
                     stage_done(s, true);
@@ -577,32 +596,36 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         mbar_wait(smem_u32(&sBar[2 + 3 * s]), ph);
                         tc_fence_after();
                         mbar_wait(smem_u32(&sBar[21 + s]), ph_res);              // the tile holds the original h_E rows again (residual)
-                        uint32_t rs[16];
-#pragma unroll
-                        for (int c16 = 0; c16 < 4; ++c16) {
-                            const uint4 t4 = *reinterpret_cast<const uint4*>(T + tile_off(r, (c0 >> 3) + c16));
-                            rs[c16 * 4] = t4.x; rs[c16 * 4 + 1] = t4.y; rs[c16 * 4 + 2] = t4.z; rs[c16 * 4 + 3] = t4.w;
-                        }
                         // pass A: v = residual + (acc + b13) in packed half, kept in registers; row statistics of those values in fp32
-                        uint32_t b3r[16];
-                        ldg256(p.b3h + c0, *reinterpret_cast<uint32_t(*)[8]>(&b3r[0]));
-                        ldg256(p.b3h + c0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&b3r[8]));
                         float sum = 0.f, sq = 0.f;
-                        uint32_t v16[16];
+                        uint32_t v16[SUBS][16];
 #pragma unroll
-                        for (int g16 = 0; g16 < 2; ++g16) {
-                            float acc[16];
-                            tmem_ld16(tmem_lane + (uint32_t)(s * 128 + g16 * 16), acc);
+                        for (int sub = 0; sub < SUBS; ++sub) {
+                            const int col = c0 + sub * 32;
+                            uint32_t rs[16];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const __half2 v = __hadd2(as_h2(rs[g16 * 8 + e]), __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(b3r[g16 * 8 + e])));
-                                const float2 vf = __half22float2(v);
-                                sum += vf.x + vf.y;
-                                sq = fmaf(vf.x, vf.x, fmaf(vf.y, vf.y, sq));
-                                v16[g16 * 8 + e] = as_u32(v);
+                            for (int c16 = 0; c16 < 4; ++c16) {
+                                const uint4 t4 = *reinterpret_cast<const uint4*>(T + tile_off(r, (col >> 3) + c16));
+                                rs[c16 * 4] = t4.x; rs[c16 * 4 + 1] = t4.y; rs[c16 * 4 + 2] = t4.z; rs[c16 * 4 + 3] = t4.w;
+                            }
+                            uint32_t b3r[16];
+                            ldg256(p.b3h + col, *reinterpret_cast<uint32_t(*)[8]>(&b3r[0]));
+                            ldg256(p.b3h + col + 16, *reinterpret_cast<uint32_t(*)[8]>(&b3r[8]));
+#pragma unroll
+                            for (int g16 = 0; g16 < 2; ++g16) {
+                                float acc[16];
+                                tmem_ld16(tmem_lane + (uint32_t)(s * 128 + sub * 32 + g16 * 16), acc);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const __half2 v = __hadd2(as_h2(rs[g16 * 8 + e]), __hadd2(as_h2(pack_sat(acc[e * 2], acc[e * 2 + 1])), as_h2(b3r[g16 * 8 + e])));
+                                    const float2 vf = __half22float2(v);
+                                    sum += vf.x + vf.y;
+                                    sq = fmaf(vf.x, vf.x, fmaf(vf.y, vf.y, sq));
+                                    v16[sub][g16 * 8 + e] = as_u32(v);
+                                }
                             }
                         }
-                        // row statistics: the four column quarters of a row exchange their partial sums through accumulator
+                        // row statistics: the column groups of a row exchange their partial sums through accumulator
                         // columns this thread has already drained (its own first two) -- tcgen05.st, one barrier, tcgen05.ld;
                         // summed in a fixed order, so the result is deterministic
 #ifdef CB2_X_NOXCHG                                                     // timing ablation: no exchange of the row statistics
@@ -613,24 +636,39 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) edge_tc_kernel(const __grid_co
                         row_quarter_sync(quarter);
                         tc_fence_after();
                         float part[8];
-                        tmem_ld2_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128), 32u, part);
+                        if (SUBS == 1) {
+                            tmem_ld2_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128), 32u, part);
+                        } else {
+                            uint32_t r4[4];
+                            const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 128);
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r4[0]), "=r"(r4[1]) : "r"(ta));
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r4[2]), "=r"(r4[3]) : "r"(ta + 64u));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part[i] = __uint_as_float(r4[i]);
+                            part[4] = part[5] = part[6] = part[7] = 0.f;
+                        }
                         const float tsum = (part[0] + part[2]) + (part[4] + part[6]), tsq = (part[1] + part[3]) + (part[5] + part[7]);
 #endif
                         const float mean = tsum * (1.0f / 128.0f);
                         const float rstd = rsqrtf(fmaxf(tsq * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-6f);
                         const __half2 rstd2 = __float2half2_rn(rstd), nmr2 = __float2half2_rn(-mean * rstd);
-                        const __half* mod_row = p.mod16 + (size_t)bmem * p.mod16_stride + c0;
                         // pass B (packed half): out = (v rstd - mean rstd) A[c] + B[c],  A = gate (1 + scale), B = gate * shift
 #pragma unroll
-                        for (int c16 = 0; c16 < 4; ++c16) {
-                            const uint4 av = __ldg(reinterpret_cast<const uint4*>(mod_row + c16 * 8));
-                            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(mod_row + 128 + c16 * 8));
-                            const uint32_t a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
-                            uint32_t o[4];
+                        for (int sub = 0; sub < SUBS; ++sub) {
+                            const int col = c0 + sub * 32;
+                            const __half* mod_row = p.mod16 + (size_t)bmem * p.mod16_stride + col;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                o[e] = as_u32(__hfma2(__hfma2(as_h2(v16[c16 * 4 + e]), rstd2, nmr2), as_h2(a4[e]), as_h2(b4[e])));
-                            *reinterpret_cast<uint4*>(T + tile_off(r, (c0 >> 3) + c16)) = make_uint4(o[0], o[1], o[2], o[3]);
+                            for (int c16 = 0; c16 < 4; ++c16) {
+                                const uint4 av = __ldg(reinterpret_cast<const uint4*>(mod_row + c16 * 8));
+                                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(mod_row + 128 + c16 * 8));
+                                const uint32_t a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+                                uint32_t o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    o[e] = as_u32(__hfma2(__hfma2(as_h2(v16[sub][c16 * 4 + e]), rstd2, nmr2), as_h2(a4[e]), as_h2(b4[e])));
+                                *reinterpret_cast<uint4*>(T + tile_off(r, (col >> 3) + c16)) = make_uint4(o[0], o[1], o[2], o[3]);
+                            }
                         }
                         stage_done(s, true);                             // tile complete: the TMA lane stores it and reloads the slot
                         mark(9, s);
